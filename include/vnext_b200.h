@@ -1,0 +1,114 @@
+/*
+ * vnext_b200 — C ABI of the B200-native (sm_100a) hot path of VNext (SeqFormer / IDOL).
+ *
+ * Plain pointers and sizes only; no torch types.  Every entry point returns 0 on success and a
+ * non-zero VNEXT_E* code on failure; vnext_last_error() returns the message for the calling thread
+ * (the reference raises RuntimeError through AT_ASSERTM / AT_ERROR at the same places; the Python
+ * binding turns a non-zero return into RuntimeError).  All `const void*` tensor arguments are
+ * DEVICE pointers on the current CUDA device unless the function name ends in `_host`.  `stream`
+ * is a cudaStream_t passed as void* (NULL = legacy default stream).  Kernels are enqueued
+ * asynchronously; nothing here synchronises the device except the `_host` variants.
+ *
+ * Reference interfaces replaced (paths under /root/reference/projects/IDOL/idol/models/ops,
+ * byte-identical copy under projects/SeqFormer/seqformer/models/ops):
+ *   vnext_msda_forward   <- ms_deform_attn_forward   src/ms_deform_attn.h:20-39,
+ *                           ms_deform_attn_cuda_forward  src/cuda/ms_deform_attn_cuda.cu:20-80,
+ *                           ms_deformable_im2col_cuda    src/cuda/ms_deform_im2col_cuda.cuh:923-954
+ *   vnext_msda_backward  <- ms_deform_attn_backward  src/ms_deform_attn.h:41-61,
+ *                           ms_deform_attn_cuda_backward src/cuda/ms_deform_attn_cuda.cu:83-152,
+ *                           ms_deformable_col2im_cuda    src/cuda/ms_deform_im2col_cuda.cuh:956-1326
+ * pybind names kept by the Python shim `MultiScaleDeformableAttention` (src/vision.cpp:13-16).
+ */
+#ifndef VNEXT_B200_H_
+#define VNEXT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* element type of value / output / grad_output / grad_value */
+enum {
+    VNEXT_F32 = 0,  /* everything fp32 (reference: AT_DISPATCH_FLOATING_TYPES float) */
+    VNEXT_F64 = 1,  /* everything fp64 (reference: double; used by gradcheck) */
+    VNEXT_BF16 = 2  /* value/output(/grad_output/grad_value) bf16; sampling_loc, attn_weight and
+                       their grads stay fp32; accumulation fp32.  New: the reference has no bf16. */
+};
+
+enum {
+    VNEXT_OK = 0,
+    VNEXT_EINVAL = 1,   /* bad argument (null pointer, non-positive size, unsupported dtype) */
+    VNEXT_ECUDA = 2,    /* CUDA runtime / launch error (message carries cudaGetErrorString) */
+    VNEXT_ENOMEM = 3
+};
+
+const char *vnext_last_error(void);
+/* "vnext_b200 <version> sm_100a" */
+const char *vnext_version(void);
+/* number of kernels this library has launched since load (all threads); for bench `gpu_launches` */
+unsigned long long vnext_launch_count(void);
+
+/*
+ * Multi-scale deformable attention, forward.
+ *   value              [batch, spatial_size, num_heads, channels]             (dtype)
+ *   spatial_shapes     int64 [num_levels, 2] = (H_l, W_l), DEVICE memory (as the reference passes it)
+ *   level_start_index  int64 [num_levels], DEVICE memory
+ *   sampling_loc       [batch, num_query, num_heads, num_levels, num_point, 2] = (x, y) in [0,1]
+ *   attn_weight        [batch, num_query, num_heads, num_levels, num_point]
+ *   output             [batch, num_query, num_heads*channels]  — fully overwritten (no pre-zeroing needed)
+ * Semantics (bit-exact indexing): h_im = y*H - 0.5, w_im = x*W - 0.5; a sample contributes only if
+ * h_im > -1 && w_im > -1 && h_im < H && w_im < W; corners outside [0,H-1]x[0,W-1] contribute 0
+ * (ms_deform_im2col_cuda.cuh:55-78, 285-288).  The reference's `im2col_step` chunking is a host loop
+ * with no numerical effect; the whole batch is one launch here.
+ */
+int vnext_msda_forward(int dtype, const void *value, const int64_t *spatial_shapes,
+                       const int64_t *level_start_index, const void *sampling_loc,
+                       const void *attn_weight, int batch, int spatial_size, int num_heads,
+                       int channels, int num_levels, int num_query, int num_point, void *output,
+                       void *stream);
+
+/*
+ * Backward.  grad_output [batch, num_query, num_heads*channels] (dtype).
+ * Outputs are fully (over)written: grad_value like value (zero-filled then accumulated with
+ * atomics, as the reference), grad_sampling_loc like sampling_loc, grad_attn_weight like attn_weight.
+ * `workspace`: only for VNEXT_BF16 — fp32 scratch of vnext_msda_backward_workspace_bytes() bytes
+ * (grad_value is accumulated in fp32 and rounded once); ignored (may be NULL) otherwise.
+ */
+int vnext_msda_backward(int dtype, const void *value, const int64_t *spatial_shapes,
+                        const int64_t *level_start_index, const void *sampling_loc,
+                        const void *attn_weight, const void *grad_output, int batch,
+                        int spatial_size, int num_heads, int channels, int num_levels,
+                        int num_query, int num_point, void *grad_value, void *grad_sampling_loc,
+                        void *grad_attn_weight, void *workspace, void *stream);
+
+size_t vnext_msda_backward_workspace_bytes(int dtype, int batch, int spatial_size, int num_heads,
+                                           int channels);
+
+/*
+ * Host-buffer variants (what a non-torch caller binds): all pointers are HOST memory (pinned or
+ * pageable); device staging buffers are owned by the library and reused across calls; the call
+ * copies inputs H2D, runs the kernel, copies outputs D2H and synchronises before returning.
+ */
+int vnext_msda_forward_host(int dtype, const void *value, const int64_t *spatial_shapes,
+                            const int64_t *level_start_index, const void *sampling_loc,
+                            const void *attn_weight, int batch, int spatial_size, int num_heads,
+                            int channels, int num_levels, int num_query, int num_point,
+                            void *output);
+
+int vnext_msda_backward_host(int dtype, const void *value, const int64_t *spatial_shapes,
+                             const int64_t *level_start_index, const void *sampling_loc,
+                             const void *attn_weight, const void *grad_output, int batch,
+                             int spatial_size, int num_heads, int channels, int num_levels,
+                             int num_query, int num_point, void *grad_value,
+                             void *grad_sampling_loc, void *grad_attn_weight);
+
+/* Which kernel variant the last forward / backward on this thread dispatched to
+ * ("fwd_f32_d32_tma", "fwd_generic", ...).  For tests and profiles. */
+const char *vnext_msda_last_variant(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VNEXT_B200_H_ */

@@ -1,0 +1,135 @@
+"""Multi-scale deformable attention operator — host side.
+
+Mirrors, name for name, the reference's operator layer:
+  * pybind module functions ``ms_deform_attn_forward`` / ``ms_deform_attn_backward``
+    (projects/IDOL/idol/models/ops/src/vision.cpp:13-16, src/ms_deform_attn.h:20-61,
+     host checks of src/cuda/ms_deform_attn_cuda.cu:28-52, 93-117)
+  * ``MSDeformAttnFunction`` (functions/ms_deform_attn_func.py:21-39)
+on top of the C ABI (include/vnext_b200.h).  Differences, all supersets:
+  * bf16 ``value`` is accepted (sampling_locations / attention_weights are used in fp32);
+  * the whole batch is one launch (``im2col_step`` is validated exactly as the reference does and
+    otherwise ignored: chunking has no numerical effect);
+  * a leading frame axis can be folded into the batch by the caller (see modules.ms_deform_attn).
+"""
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _cabi
+
+_DTYPES = {torch.float32: _cabi.F32, torch.float64: _cabi.F64, torch.bfloat16: _cabi.BF16}
+
+
+def _require(cond, msg):
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step):
+    named = (("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+             ("sampling_loc", sampling_loc), ("attn_weight", attn_weight))
+    if not value.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")          # ms_deform_attn.h:38
+    for name, t in named:
+        _require(t.is_contiguous(), f"{name} tensor has to be contiguous")
+    for name, t in named:
+        _require(t.is_cuda, f"{name} must be a CUDA tensor")
+    _require(value.dtype in _DTYPES, f"ms_deform_attn: unsupported dtype {value.dtype}")
+    _require(spatial_shapes.dtype == torch.int64 and level_start_index.dtype == torch.int64,
+             "spatial_shapes and level_start_index must be int64 tensors")
+    _require(value.dim() == 4 and sampling_loc.dim() == 6 and attn_weight.dim() == 5,
+             "expected value [N,S,M,D], sampling_loc [N,Lq,M,L,P,2], attn_weight [N,Lq,M,L,P]")
+    batch = value.size(0)
+    step = min(batch, int(im2col_step))
+    _require(batch == 0 or (step > 0 and batch % step == 0),
+             f"batch({batch}) must divide im2col_step({step})")   # ms_deform_attn_cuda.cu:52
+    N, S, M, D = value.shape
+    L = spatial_shapes.size(0)
+    Lq, P = sampling_loc.size(1), sampling_loc.size(4)
+    _require(tuple(sampling_loc.shape) == (N, Lq, M, L, P, 2) and tuple(attn_weight.shape) == (N, Lq, M, L, P),
+             "sampling_loc / attn_weight shapes do not match value / spatial_shapes")
+    return N, S, M, D, L, Lq, P
+
+
+def _loc_dtype(value):
+    return torch.float64 if value.dtype == torch.float64 else torch.float32
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step):
+    N, S, M, D, L, Lq, P = _check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                         im2col_step)
+    ldt = _loc_dtype(value)
+    if sampling_loc.dtype != ldt:
+        sampling_loc = sampling_loc.to(ldt)
+    if attn_weight.dtype != ldt:
+        attn_weight = attn_weight.to(ldt)
+    out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        rc = _cabi.lib().vnext_msda_forward(
+            _DTYPES[value.dtype], value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            sampling_loc.data_ptr(), attn_weight.data_ptr(), N, S, M, D, L, Lq, P, out.data_ptr(), _stream(value))
+    _cabi.check(rc, "ms_deform_attn_forward")
+    return out
+
+
+def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                            im2col_step):
+    N, S, M, D, L, Lq, P = _check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                         im2col_step)
+    _require(grad_output.is_contiguous(), "grad_output tensor has to be contiguous")
+    _require(grad_output.is_cuda, "grad_output must be a CUDA tensor")
+    _require(grad_output.dtype == value.dtype and grad_output.numel() == N * Lq * M * D,
+             "grad_output must match the forward output")
+    ldt = _loc_dtype(value)
+    loc_in, attn_in = sampling_loc.to(ldt), attn_weight.to(ldt)
+    grad_value = torch.empty_like(value)
+    grad_loc = torch.empty(sampling_loc.shape, dtype=ldt, device=value.device)
+    grad_attn = torch.empty(attn_weight.shape, dtype=ldt, device=value.device)
+    ws = None
+    ws_ptr = None
+    if value.dtype == torch.bfloat16:
+        ws = torch.empty(value.shape, dtype=torch.float32, device=value.device)
+        ws_ptr = ws.data_ptr()
+    with torch.cuda.device(value.device):
+        rc = _cabi.lib().vnext_msda_backward(
+            _DTYPES[value.dtype], value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            loc_in.data_ptr(), attn_in.data_ptr(), grad_output.data_ptr(), N, S, M, D, L, Lq, P,
+            grad_value.data_ptr(), grad_loc.data_ptr(), grad_attn.data_ptr(), ws_ptr, _stream(value))
+    _cabi.check(rc, "ms_deform_attn_backward")
+    if grad_loc.dtype != sampling_loc.dtype:
+        grad_loc = grad_loc.to(sampling_loc.dtype)
+    if grad_attn.dtype != attn_weight.dtype:
+        grad_attn = grad_attn.to(attn_weight.dtype)
+    return [grad_value, grad_loc, grad_attn]
+
+
+class MSDeformAttnFunction(Function):
+    """Same call signature and gradient contract as functions/ms_deform_attn_func.py:21-39."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
+                im2col_step):
+        ctx.im2col_step = im2col_step
+        output = ms_deform_attn_forward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                                        attention_weights, ctx.im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                              attention_weights)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, lsi, loc, attn = ctx.saved_tensors
+        grad_output = grad_output.contiguous()
+        grad_value, grad_loc, grad_attn = ms_deform_attn_backward(value, shapes, lsi, loc, attn, grad_output,
+                                                                  ctx.im2col_step)
+        return grad_value, None, None, grad_loc, grad_attn, None
+
+
+def ms_deform_attn(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, im2col_step=64):
+    return MSDeformAttnFunction.apply(value, spatial_shapes, level_start_index, sampling_locations,
+                                      attention_weights, im2col_step)
