@@ -119,16 +119,7 @@ def backward_torch(value, shapes, loc, attn, grad_out):
     return v.grad, lc.grad, aw.grad
 
 
-def make_inputs(N, Lq, M, D, shapes, P, seed, dtype=torch.float32, loc_range=(0.0, 1.0)):
-    """Input recipe of the reference test (ops/test.py:33-36): value~U(0,.01), loc~U, attn normalised."""
-    g = torch.Generator().manual_seed(seed)
-    shapes_t = torch.as_tensor(shapes, dtype=torch.long)
-    L = shapes_t.shape[0]
-    lsi = torch.cat((shapes_t.new_zeros((1,)), shapes_t.prod(1).cumsum(0)[:-1]))
-    S = int(shapes_t.prod(1).sum())
-    value = torch.rand(N, S, M, D, generator=g) * 0.01
-    lo, hi = loc_range
-    loc = torch.rand(N, Lq, M, L, P, 2, generator=g) * (hi - lo) + lo
-    attn = torch.rand(N, Lq, M, L, P, generator=g) + 1e-5
-    attn = attn / attn.sum(-1, keepdim=True).sum(-2, keepdim=True)
-    return value.to(dtype), shapes_t, lsi, loc.to(dtype), attn.to(dtype)
+def make_inputs(*args, **kwargs):
+    """Input recipe of the reference test (ops/test.py:33-36); shared with bench.py via vnext_b200.synth."""
+    from vnext_b200.synth import make_msda_inputs
+    return make_msda_inputs(*args, **kwargs)

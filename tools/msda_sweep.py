@@ -16,7 +16,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle.msda_oracle import make_inputs  # noqa: E402  (input recipe only)
+from vnext_b200.synth import make_msda_inputs as make_inputs  # noqa: E402
 from vnext_b200 import msda  # noqa: E402
 
 PYR = {"480x864": [(60, 108), (30, 54), (15, 27), (8, 14)], "736x1280": [(92, 160), (46, 80), (23, 40), (12, 20)]}

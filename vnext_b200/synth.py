@@ -1,0 +1,102 @@
+"""Synthetic inputs and weights (no datasets or checkpoints exist offline): used by bench.py, the
+tests, the golden-vector scripts and the oracle alike.  Nothing here computes any part of the hot path.
+
+Deterministic synthetic weights keyed by state-dict name:
+
+There are no checkpoints offline, and a seeded `reset_parameters()` depends on module construction
+order (which differs between the reference's module tree and this repo's engine).  So every tensor of
+a state dict is filled from a generator seeded by crc32(key): the reference model (in
+tests/golden/make_*_golden.py), the CPU oracle and the CUDA engine all get bit-identical weights from
+the key names alone.  Distributions keep activations O(1) through 50+ layers and — unlike the
+reference's init, which zeroes `sampling_offsets.weight` / `attention_weights.*` — make every
+parameter matter, so parity tests exercise data-dependent sampling locations.
+"""
+import zlib
+
+import torch
+
+
+def _gen(key, seed):
+    return torch.Generator().manual_seed((zlib.crc32(key.encode()) + 7919 * seed) % (2 ** 31))
+
+
+def fill_tensor(key, shape, seed=0, dtype=torch.float32):
+    g = _gen(key, seed)
+    shape = tuple(shape)
+    leaf = key.rsplit(".", 1)[-1]
+
+    def randn(std=1.0, mean=0.0):
+        return (torch.randn(shape, generator=g) * std + mean).to(dtype)
+
+    def uniform(lo, hi):
+        return (torch.rand(shape, generator=g) * (hi - lo) + lo).to(dtype)
+
+    if leaf == "relative_position_index" or leaf == "num_batches_tracked":
+        raise KeyError(key)                     # integer buffers are structural, never synthesised
+    if leaf == "running_var":
+        return uniform(0.5, 1.5)
+    if leaf == "running_mean":
+        return randn(0.1)
+    is_norm = (".norm" in key or "norm." in key or key.split(".")[-2].startswith("norm")
+               or (".input_proj." in key and key.split(".")[-2] == "1"))
+    if len(shape) == 1:
+        if leaf == "weight":                     # affine scale of BN / GN / LN
+            return uniform(0.8, 1.2)
+        if "sampling_offsets" in key:            # pixel-scale offsets so samples spread over cells
+            return randn(1.5)
+        if "class_embed" in key:
+            return randn(0.5, -2.0)
+        if is_norm:
+            return randn(0.05)
+        return randn(0.05)
+    if "query_embed" in key or "level_embed" in key or "relative_position_bias_table" in key:
+        return randn(1.0 if "relative_position_bias_table" not in key else 0.2)
+    fan_in = 1
+    for s in shape[1:]:
+        fan_in *= s
+    std = 1.0 / (fan_in ** 0.5)
+    if "sampling_offsets" in key:
+        std *= 0.5
+    if "bbox_embed" in key and key.split(".")[-2] == "2":
+        std *= 0.3
+    if "controller" in key and key.split(".")[-2] == "2":
+        std *= 0.5
+    if "backbone" in key and len(shape) == 4:    # ReLU networks: He scaling keeps the signal alive
+        std *= 2 ** 0.5
+        if key.endswith("conv3.weight"):
+            std *= 0.5                            # residual branches add up; keep res5 bounded
+    return randn(std)
+
+
+def fill_state_dict(spec, seed=0):
+    """spec: dict key -> shape (or tensor).  Integer / structural buffers are passed through."""
+    out = {}
+    for k, v in spec.items():
+        if isinstance(v, torch.Tensor) and not v.dtype.is_floating_point:
+            out[k] = v.clone()
+            continue
+        shape = v.shape if isinstance(v, torch.Tensor) else v
+        out[k] = fill_tensor(k, shape, seed)
+    return out
+
+
+def synthetic_clip(num_frames, height, width, seed=0):
+    """uint8-valued float frames, the bench's `data: synthetic` (SURVEY §8d cfg 2)."""
+    g = torch.Generator().manual_seed(1234 + seed)
+    return [torch.randint(0, 256, (3, height, width), generator=g).float() for _ in range(num_frames)]
+
+
+def make_msda_inputs(N, Lq, M, D, shapes, P, seed, dtype=torch.float32, loc_range=(0.0, 1.0)):
+    """MSDA input recipe of the reference test (projects/IDOL/idol/models/ops/test.py:33-36):
+    value ~ U(0, .01), sampling locations ~ U(loc_range), attention weights normalised over (L, P)."""
+    g = torch.Generator().manual_seed(seed)
+    shapes_t = torch.as_tensor(shapes, dtype=torch.long)
+    L = shapes_t.shape[0]
+    lsi = torch.cat((shapes_t.new_zeros((1,)), shapes_t.prod(1).cumsum(0)[:-1]))
+    S = int(shapes_t.prod(1).sum())
+    value = torch.rand(N, S, M, D, generator=g) * 0.01
+    lo, hi = loc_range
+    loc = torch.rand(N, Lq, M, L, P, 2, generator=g) * (hi - lo) + lo
+    attn = torch.rand(N, Lq, M, L, P, generator=g) + 1e-5
+    attn = attn / attn.sum(-1, keepdim=True).sum(-2, keepdim=True)
+    return value.to(dtype), shapes_t, lsi, loc.to(dtype), attn.to(dtype)
