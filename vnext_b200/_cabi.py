@@ -53,3 +53,48 @@ def launch_count():
 
 def last_variant():
     return lib().vnext_msda_last_variant().decode()
+
+
+# ------------------------------------------------------------------ optional per-kernel CUDA-event timing
+class KernelTimer:
+    """When active, every C-ABI kernel call site brackets its launch with CUDA events on the launching
+    stream.  bench.py uses it on a few eager (non-graph) steps to get the live per-kernel durations the
+    roofline line is computed from; it is off in the timed region."""
+    active = None
+
+    def __init__(self):
+        self.records = []          # (name, info dict, start_event, end_event)
+
+    def __enter__(self):
+        KernelTimer.active = self
+        return self
+
+    def __exit__(self, *exc):
+        KernelTimer.active = None
+
+    def summary(self):
+        import torch
+        torch.cuda.synchronize()
+        agg = {}
+        for name, info, a, b in self.records:
+            d = agg.setdefault(name, {"calls": 0, "us": 0.0, "bytes": 0.0, "flops": 0.0})
+            d["calls"] += 1
+            d["us"] += a.elapsed_time(b) * 1e3
+            d["bytes"] += info.get("bytes", 0.0)
+            d["flops"] += info.get("flops", 0.0)
+        return agg
+
+
+def timed_call(name, info, stream_tensor, fn):
+    """Run fn() (which enqueues exactly one library call) with optional event bracketing."""
+    kt = KernelTimer.active
+    if kt is None:
+        return fn()
+    import torch
+    st = torch.cuda.current_stream(stream_tensor.device)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(st)
+    rc = fn()
+    b.record(st)
+    kt.records.append((name, info, a, b))
+    return rc

@@ -68,10 +68,16 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     if attn_weight.dtype != ldt:
         attn_weight = attn_weight.to(ldt)
     out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+    e = value.element_size()
+    info = {"bytes": float(N) * (e * S * M * D + sampling_loc.element_size() * 3 * Lq * M * L * P + e * Lq * M * D),
+            "N": N, "Lq": Lq, "S": S}
     with torch.cuda.device(value.device):
-        rc = _cabi.lib().vnext_msda_forward(
-            _DTYPES[value.dtype], value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
-            sampling_loc.data_ptr(), attn_weight.data_ptr(), N, S, M, D, L, Lq, P, out.data_ptr(), _stream(value))
+        rc = _cabi.timed_call(
+            "msda_fwd_enc" if Lq == S else "msda_fwd_dec", info, value,
+            lambda: _cabi.lib().vnext_msda_forward(
+                _DTYPES[value.dtype], value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                sampling_loc.data_ptr(), attn_weight.data_ptr(), N, S, M, D, L, Lq, P, out.data_ptr(),
+                _stream(value)))
     _cabi.check(rc, "ms_deform_attn_forward")
     return out
 

@@ -1,0 +1,108 @@
+"""`SeqFormer` META_ARCH facade with the reference's model API (projects/SeqFormer/seqformer/seqformer.py).
+
+`SeqFormer.forward(batched_inputs)` in eval mode takes the same `list[dict]` the reference's
+YTVISDatasetMapper produces — {"image": [Tensor CHW x T], "height", "width", "file_names"} — and returns
+the same dict {"image_size", "pred_scores", "pred_labels", "pred_masks"} (seqformer.py:226-235, 403-410),
+running the B200 engine underneath.  When detectron2 is importable the class registers itself under
+META_ARCH_REGISTRY as "SeqFormer" (detectron2/modeling/meta_arch/build.py:16-25), so
+`cfg.MODEL.META_ARCHITECTURE: "SeqFormer"` in projects/SeqFormer/train_net.py resolves to it unchanged.
+Training (`self.training`) is not part of this round's path and raises.
+"""
+import torch
+from torch import nn
+
+from .engine import SeqFormerEngine
+from .runner import ClipRunner
+from .state_spec import seqformer_r50_state_spec
+
+
+class SeqFormer(nn.Module):
+    def __init__(self, cfg=None, state_dict=None, device="cuda", precision="tf32", **overrides):
+        super().__init__()
+        g = (lambda path, default: _cfg_get(cfg, path, default)) if cfg is not None else (lambda path, default: default)
+        self.num_frames = g("INPUT.SAMPLING_FRAME_NUM", 5)
+        self.num_classes = g("MODEL.SeqFormer.NUM_CLASSES", 40)
+        self.num_queries = g("MODEL.SeqFormer.NUM_OBJECT_QUERIES", 300)
+        self.mask_stride = g("MODEL.SeqFormer.MASK_STRIDE", 4)
+        self.is_multi_cls = g("MODEL.SeqFormer.MULTI_CLS_ON", True)
+        self.apply_cls_thres = g("MODEL.SeqFormer.APPLY_CLS_THRES", 0.05)
+        self.clip_matching = g("MODEL.SeqFormer.CLIP_MATCHING", False)
+        self.pixel_mean = tuple(g("MODEL.PIXEL_MEAN", (123.675, 116.280, 103.530)))
+        self.pixel_std = tuple(g("MODEL.PIXEL_STD", (58.395, 57.120, 57.375)))
+        self.device_name = g("MODEL.DEVICE", device)
+        self.precision = precision
+        self.__dict__.update(overrides)
+        self.engine = None
+        self._runners = {}
+        if state_dict is not None:
+            self.load_reference_state_dict(state_dict)
+
+    def expected_state_spec(self):
+        return seqformer_r50_state_spec(self.num_queries, self.num_classes)
+
+    def load_reference_state_dict(self, state_dict):
+        """Takes a reference-layout checkpoint (`model` dict of a DetectionCheckpointer .pth)."""
+        spec = self.expected_state_spec()
+        missing = [k for k in spec if k not in state_dict]
+        if missing:
+            raise KeyError(f"checkpoint is missing {len(missing)} keys, e.g. {missing[:3]}")
+        for k, shp in spec.items():
+            if tuple(state_dict[k].shape) != tuple(shp):
+                raise ValueError(f"{k}: expected shape {tuple(shp)}, got {tuple(state_dict[k].shape)}")
+        self.engine = SeqFormerEngine(state_dict, device=self.device_name, pixel_mean=self.pixel_mean,
+                                      pixel_std=self.pixel_std, mask_stride=self.mask_stride,
+                                      precision=self.precision)
+        self._runners = {}
+
+    def runner(self, T, H, W, ori_size):
+        key = (T, H, W, tuple(ori_size))
+        if key not in self._runners:
+            self._runners[key] = ClipRunner(self.engine, T, H, W, ori_size)
+        return self._runners[key]
+
+    def forward(self, batched_inputs):
+        if self.training:
+            raise NotImplementedError("vnext_b200 SeqFormer: the training step is not on this round's hot path")
+        if self.engine is None:
+            raise RuntimeError("no weights loaded: call load_reference_state_dict(checkpoint['model'])")
+        if self.clip_matching:
+            raise NotImplementedError("CLIP_MATCHING inference (seqformer.py:236-262) is out of scope (SURVEY §8f)")
+        video = batched_inputs[0]
+        frames = video["image"]
+        T = len(frames)
+        H, W = frames[0].shape[-2:]
+        ori = (video.get("height", H), video.get("width", W))
+        run = self.runner(T, H, W, ori)
+        stage = run.frames_pin
+        for i, f in enumerate(frames):              # uint8-valued frames (float or uint8 tensors) -> pinned staging
+            stage[i].copy_(f)
+        scores, masks = run.run_host()
+        return SeqFormerEngine.finish_video(scores, masks, ori, self.apply_cls_thres, self.is_multi_cls)
+
+
+def _cfg_get(cfg, path, default):
+    node = cfg
+    for part in path.split("."):
+        if isinstance(node, dict):
+            if part not in node:
+                return default
+            node = node[part]
+        else:
+            if not hasattr(node, part):
+                return default
+            node = getattr(node, part)
+    return node
+
+
+def register_with_detectron2():
+    """Register under the reference's registry name; returns False when detectron2 is absent."""
+    try:
+        from detectron2.modeling import META_ARCH_REGISTRY
+    except Exception:
+        return False
+    if "SeqFormer" not in META_ARCH_REGISTRY:
+        META_ARCH_REGISTRY.register(SeqFormer)
+    return True
+
+
+register_with_detectron2()
