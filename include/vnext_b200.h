@@ -104,6 +104,21 @@ int vnext_msda_backward_host(int dtype, const void *value, const int64_t *spatia
                              int num_query, int num_point, void *grad_value,
                              void *grad_sampling_loc, void *grad_attn_weight);
 
+/*
+ * Linear layer / 1x1 convolution on the tcgen05 tensor cores with a fused epilogue:
+ *     out[M, N] = epilogue( a[M, K] . weight[N, K]^T + bias[N] )
+ * fp32 storage, TF32 tensor-core math, fp32 accumulation.  `weight` is the nn.Linear / 1x1-conv weight as
+ * the reference checkpoint stores it.  Replaces F.linear + separate bias/ReLU/residual/LayerNorm kernels of
+ * projects/SeqFormer/seqformer/models/deformable_transformer.py:155-169 (forward_ffn, norm1/norm2) and
+ * models/ops/modules/ms_deform_attn.py:94-100,114 (value/offset/weight/output projections).
+ *   epilogue 0: + bias            1: relu(+ bias)
+ *            2: LayerNorm(+ bias + residual[M, ldr]) * ln_gamma + ln_beta   (needs N == 256)
+ * lda / ldo / ldr are row pitches in elements (multiples of 4); all pointers 16-byte aligned device memory.
+ */
+int vnext_linear_tf32(const float *a, int lda, const float *weight, const float *bias, const float *residual,
+                      int ldr, const float *ln_gamma, const float *ln_beta, float ln_eps, float *out, int ldo,
+                      int M, int N, int K, int epilogue, void *stream);
+
 /* Which kernel variant the last forward / backward on this thread dispatched to
  * ("fwd_f32_d32_tma", "fwd_generic", ...).  For tests and profiles. */
 const char *vnext_msda_last_variant(void);

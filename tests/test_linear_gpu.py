@@ -1,0 +1,59 @@
+"""GPU numerics of the tcgen05 linear kernel vs a plain PyTorch fp32 reference of the same op."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120)]
+
+
+def _mk(M, N, K, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g) * 0.1
+    return x.cuda(), w.cuda(), b.cuda()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 256), (300, 256, 256), (1000, 384, 256), (97800, 256, 256),
+                                   (4097, 1024, 256), (513, 256, 1024), (77, 64, 64), (1500, 128, 2048), (5, 169, 256)])
+def test_bias_and_relu(M, N, K):
+    from vnext_b200.linear import linear
+    torch.backends.cuda.matmul.allow_tf32 = False
+    x, w, b = _mk(M, N, K)
+    ref = F.linear(x.double(), w.double(), b.double())
+    out = linear(x, w, b)
+    # TF32 inputs (10-bit mantissa): error ~ 2^-11 * sqrt(K) * |x||w| per term; bound relative to output scale
+    tol = 2e-3 * ref.abs().max().item()
+    assert (out.double() - ref).abs().max().item() < tol
+    out_r = linear(x, w, b, relu=True)
+    assert (out_r.double() - ref.clamp(min=0)).abs().max().item() < tol
+    out_nb = linear(x, w, None)
+    assert (out_nb.double() - F.linear(x.double(), w.double())).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("M,K", [(128, 256), (333, 1024), (97800, 256)])
+def test_residual_layernorm_epilogue(M, K):
+    from vnext_b200.linear import linear
+    x, w, b = _mk(M, 256, K, 1)
+    g = torch.Generator().manual_seed(2)
+    res = torch.randn(M, 256, generator=g).cuda()
+    gamma = (torch.rand(256, generator=g) + 0.5).cuda()
+    beta = (torch.randn(256, generator=g) * 0.1).cuda()
+    ref = F.layer_norm(res.double() + F.linear(x.double(), w.double(), b.double()), (256,), gamma.double(),
+                       beta.double(), 1e-5)
+    out = linear(x, w, b, residual=res, ln_weight=gamma, ln_bias=beta)
+    assert (out.double() - ref).abs().max().item() < 3e-3
+
+
+def test_strided_views_and_errors():
+    from vnext_b200.linear import linear
+    x, w, b = _mk(256, 256, 256, 3)
+    big = torch.zeros(256, 512, device="cuda")
+    big[:, :256] = x
+    out = linear(big[:, :256], w, b)                      # lda = 512
+    ref = F.linear(x.double(), w.double(), b.double())
+    assert (out.double() - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
+    with pytest.raises(RuntimeError, match="N == 256"):
+        linear(x, torch.randn(384, 256, device="cuda"), torch.zeros(384, device="cuda"),
+               residual=torch.zeros(256, 384, device="cuda"), ln_weight=torch.ones(384, device="cuda"),
+               ln_bias=torch.zeros(384, device="cuda"))

@@ -1,0 +1,410 @@
+// Dense linear layers / 1x1 convolutions on the 5th-generation tensor cores (sm_100a).
+//
+//   out[M, N] = epilogue( A[M, K] . B[N, K]^T + bias[N] )
+//
+// A = activations (tokens or NHWC pixels, K contiguous), B = the nn.Linear / 1x1-conv weight exactly as
+// the checkpoint stores it ([out, in], K contiguous).  fp32 storage, TF32 tensor-core math with fp32
+// accumulation in TMEM (kind::tf32) — the precision PyTorch's own conv path uses on this GPU; a bf16
+// instantiation shares the code.
+//
+// Replaces the cuBLAS GEMM + separate bias / ReLU / residual-add / LayerNorm kernels of the reference's
+// projection and FFN layers (projects/SeqFormer/seqformer/models/deformable_transformer.py:155-169,
+// ops/modules/ms_deform_attn.py:94-100,114) with ONE kernel per layer:
+//   * warp 0   : TMA producer   (cp.async.bulk.tensor.2d, SWIZZLE_128B, 4-stage mbarrier ring)
+//   * warp 1   : MMA issuer     (one elected thread, tcgen05.mma cta_group::1, M=128 x N=BLOCK_N x K=32B)
+//   * warp 2   : TMEM allocator (2 accumulator stages so the epilogue of tile i overlaps the MMAs of i+1)
+//   * warps 4-7: epilogue       (tcgen05.ld: TMEM lane == output row, so each thread owns a whole row
+//                                slice: bias, ReLU, and — when N == BLOCK_N == 256 — residual add +
+//                                LayerNorm with thread-local statistics, no cross-thread reduction)
+//   * persistent grid, static round-robin over (m, n) tiles, n fastest so neighbouring CTAs share A in L2.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace vnext {
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {   // arrives on `bar` when all prior MMAs of this thread retire
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+template <int KIND>   // 0 = tf32, 1 = f16/bf16
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if (KIND == 0) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+// 32 lanes x 32 consecutive 32-bit columns: thread t of the warp gets columns [c, c+32) of TMEM lane (warp%4)*32 + t
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+        "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
+        "%25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+        "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+        "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile in shared memory, 128-byte rows, SWIZZLE_128B (8 rows x 128 B = 1024-B atoms):
+//   start address >> 4 | LBO (ignored for swizzled K-major) = 1 | SBO = 1024 B between 8-row groups | version 1 | layout 2
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// c_format F32 (1) @4 | a_format @7 | b_format @10 | K-major A, B (0) @15,16 | N>>3 @17 | M>>4 @24
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+enum { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_BIAS_RES_LN = 2 };
+
+struct GemmParams {
+    int M, N, K;
+    const float *bias;       // [N] or null
+    const float *residual;   // [M, ldr] (EPI_BIAS_RES_LN)
+    const float *gamma;      // [N]
+    const float *beta;       // [N]
+    float *out;              // [M, ldo]
+    int ldo, ldr;
+    int mode;
+    float eps;
+    int num_m_tiles, num_n_tiles;
+};
+
+constexpr int kGemmThreads = 256;
+constexpr int BLOCK_M = 128;
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+    constexpr int BLOCK_K = 32;                 // fp32 elements = 128 bytes = one swizzle row
+    constexpr int UMMA_K = 8;                   // 32 bytes of tf32
+    constexpr int A_BYTES = BLOCK_M * 128, B_BYTES = BLOCK_N * 128;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int ACC_STAGES = 2;
+    constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;          // 256 or 512: power of two >= 32
+    constexpr uint32_t IDESC = make_idesc(2, BLOCK_M, BLOCK_N);
+    static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
+
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[ACC_STAGES], tmem_empty[ACC_STAGES];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_a);
+        prefetch_tmap(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+#pragma unroll
+        for (int s = 0; s < ACC_STAGES; ++s) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                     "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0 && lane == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0, phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_idx = (tile / p.num_n_tiles) * BLOCK_M, n_idx = (tile % p.num_n_tiles) * BLOCK_N;
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                unsigned char *sa = smem + stage * STAGE_BYTES, *sb = sa + A_BYTES;
+                mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                tma_load_2d(sa, &tmap_a, kb * BLOCK_K, m_idx, &full_bar[stage]);
+                tma_load_2d(sb, &tmap_b, kb * BLOCK_K, n_idx, &full_bar[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===================== MMA issuer =====================
+        int stage = 0, phase = 0, acc = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            tcgen05_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tcgen05_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
+                const uint64_t da = make_smem_desc_sw128(sa), db = make_smem_desc_sw128(sb);
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k)   // advance 32 B inside the 128-B swizzle row: +2 in 16-B units
+                    umma<0>(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0);
+                umma_commit(&empty_bar[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&tmem_full[acc]);
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int ew = warp - 4;                                   // TMEM lane quarter this warp may touch
+        int acc = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_idx = (tile / p.num_n_tiles) * BLOCK_M, n_idx = (tile % p.num_n_tiles) * BLOCK_N;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+            const int row = m_idx + ew * 32 + lane;
+            const bool row_ok = row < p.M;
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
+            float *orow = p.out + (size_t)row * p.ldo + n_idx;
+            if (p.mode == EPI_BIAS_RES_LN) {
+                // pass 1: x = acc + bias + residual, parked back in TMEM; thread-local mean / variance
+                const float *rrow = p.residual + (size_t)row * p.ldr + n_idx;
+                float sum = 0.f, sumsq = 0.f;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (row_ok) r = *reinterpret_cast<const float4 *>(rrow + c0 + j);
+                        const float4 b = *reinterpret_cast<const float4 *>(p.bias + n_idx + c0 + j);
+                        float x0 = __uint_as_float(v[j]) + b.x + r.x, x1 = __uint_as_float(v[j + 1]) + b.y + r.y;
+                        float x2 = __uint_as_float(v[j + 2]) + b.z + r.z, x3 = __uint_as_float(v[j + 3]) + b.w + r.w;
+                        sum += (x0 + x1) + (x2 + x3);
+                        sumsq += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
+                        v[j] = __float_as_uint(x0); v[j + 1] = __float_as_uint(x1);
+                        v[j + 2] = __float_as_uint(x2); v[j + 3] = __float_as_uint(x3);
+                    }
+                    tmem_st32(taddr + c0, v);
+                }
+                tmem_st_wait();
+                const float mean = sum * (1.f / BLOCK_N);
+                const float var = fmaxf(sumsq * (1.f / BLOCK_N) - mean * mean, 0.f);
+                const float rstd = rsqrtf(var + p.eps);
+#pragma unroll 1
+                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    tmem_ld_wait();
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 g = *reinterpret_cast<const float4 *>(p.gamma + n_idx + c0 + j);
+                            const float4 be = *reinterpret_cast<const float4 *>(p.beta + n_idx + c0 + j);
+                            float4 o;
+                            o.x = (__uint_as_float(v[j]) - mean) * rstd * g.x + be.x;
+                            o.y = (__uint_as_float(v[j + 1]) - mean) * rstd * g.y + be.y;
+                            o.z = (__uint_as_float(v[j + 2]) - mean) * rstd * g.z + be.z;
+                            o.w = (__uint_as_float(v[j + 3]) - mean) * rstd * g.w + be.w;
+                            *reinterpret_cast<float4 *>(orow + c0 + j) = o;
+                        }
+                    }
+                }
+            } else {
+                const bool relu = p.mode == EPI_BIAS_RELU;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    tmem_ld_wait();
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const int col = n_idx + c0 + j;
+                            if (col + 3 < p.N) {
+                                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (p.bias) b = *reinterpret_cast<const float4 *>(p.bias + col);
+                                float4 o = make_float4(__uint_as_float(v[j]) + b.x, __uint_as_float(v[j + 1]) + b.y,
+                                                       __uint_as_float(v[j + 2]) + b.z, __uint_as_float(v[j + 3]) + b.w);
+                                if (relu) {
+                                    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                                }
+                                *reinterpret_cast<float4 *>(orow + c0 + j) = o;
+                            } else {
+#pragma unroll
+                                for (int t = 0; t < 4; ++t)
+                                    if (col + t < p.N) {
+                                        float o = __uint_as_float(v[j + t]) + (p.bias ? p.bias[col + t] : 0.f);
+                                        orow[c0 + j + t] = relu ? fmaxf(o, 0.f) : o;
+                                    }
+                            }
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    }
+    return fn;
+}
+
+// 2-D fp32 row-major [rows, cols] with row pitch ld (elements); box = [box_rows, 32 columns (128 B)], SWIZZLE_128B
+static int make_tmap_f32(CUtensorMap *tm, const float *ptr, int rows, int cols, int ld, int box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return VNEXT_ECUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for [%d x %d] ld %d", (int)r, rows, cols, ld);
+        return VNEXT_ECUDA;
+    }
+    return VNEXT_OK;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, GemmParams p, cudaStream_t stream) {
+    auto kern = gemm_tf32_kernel<BLOCK_N, STAGES>;
+    constexpr size_t smem = (size_t)STAGES * (BLOCK_M * 128 + BLOCK_N * 128) + 1024;
+    static bool configured = false;
+    if (!configured) {
+        VNEXT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    p.num_m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+    p.num_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    kern<<<grid, kGemmThreads, smem, stream>>>(ta, tb, p);
+    count_launch();
+    VNEXT_CUDA(cudaGetLastError());
+    return VNEXT_OK;
+}
+
+int linear_tf32_device(const float *a, int lda, const float *w, const float *bias, const float *residual, int ldr,
+                       const float *gamma, const float *beta, float eps, float *out, int ldo, int M, int N, int K,
+                       int mode, cudaStream_t stream) {
+    if (M == 0 || N == 0) return VNEXT_OK;
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K; p.bias = bias; p.residual = residual; p.gamma = gamma; p.beta = beta; p.out = out;
+    p.ldo = ldo; p.ldr = ldr; p.mode = mode; p.eps = eps; p.num_m_tiles = p.num_n_tiles = 0;
+    const bool wide = (N % 256 == 0);
+    if (mode == EPI_BIAS_RES_LN && N != 256) {
+        set_error("vnext_linear: the fused residual+LayerNorm epilogue needs N == 256 (got %d)", N);
+        return VNEXT_EINVAL;
+    }
+    CUtensorMap ta, tb;
+    int rc = make_tmap_f32(&ta, a, M, K, lda, BLOCK_M);
+    if (rc) return rc;
+    rc = make_tmap_f32(&tb, w, N, K, K, wide ? 256 : 128);
+    if (rc) return rc;
+    return wide ? launch_gemm<256, 4>(ta, tb, p, stream) : launch_gemm<128, 6>(ta, tb, p, stream);
+}
+
+}  // namespace vnext
+
+using namespace vnext;
+
+extern "C" int vnext_linear_tf32(const float *a, int lda, const float *weight, const float *bias, const float *residual,
+                                 int ldr, const float *ln_gamma, const float *ln_beta, float ln_eps, float *out,
+                                 int ldo, int M, int N, int K, int epilogue, void *stream) {
+    VNEXT_CHECK_ARG(M >= 0 && N >= 0 && K > 0, "vnext_linear_tf32: bad sizes M=%d N=%d K=%d", M, N, K);
+    VNEXT_CHECK_ARG(epilogue >= 0 && epilogue <= 2, "vnext_linear_tf32: unknown epilogue %d", epilogue);
+    if (M == 0 || N == 0) return VNEXT_OK;
+    VNEXT_CHECK_ARG(a && weight && out, "vnext_linear_tf32: null pointer");
+    VNEXT_CHECK_ARG((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(weight) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(out) & 15) == 0 && lda % 4 == 0 && K % 4 == 0 && ldo % 4 == 0,
+                    "vnext_linear_tf32: pointers must be 16-byte aligned and lda, K, ldo multiples of 4");
+    VNEXT_CHECK_ARG(!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "vnext_linear_tf32: bias must be 16-B aligned");
+    if (epilogue == EPI_BIAS_RES_LN)
+        VNEXT_CHECK_ARG(bias && residual && ln_gamma && ln_beta && ldr % 4 == 0 &&
+                            (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
+                        "vnext_linear_tf32: residual+LayerNorm epilogue needs bias, residual, gamma, beta (16-B aligned)");
+    return linear_tf32_device(a, lda, weight, bias, residual, ldr, ln_gamma, ln_beta, ln_eps, out, ldo, M, N, K, epilogue,
+                              static_cast<cudaStream_t>(stream));
+}

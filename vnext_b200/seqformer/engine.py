@@ -462,9 +462,10 @@ class SeqFormerEngine:
         if multi_cls:
             above = torch.where(valid_scores > apply_cls_thres)
             scores, labels = valid_scores[above], above[1]
-            out_masks = masks[above[0]]
+            # the reference materialises masks[above[0]] (one copy per (query, class) hit); views are equivalent
+            out_masks = [masks[i] for i in above[0].tolist()]
         else:
             scores, labels = valid_scores.max(-1)
-            out_masks = masks
+            out_masks = [m for m in masks]
         return {"image_size": tuple(ori_size), "pred_scores": scores.tolist(), "pred_labels": labels.tolist(),
-                "pred_masks": [m for m in out_masks]}
+                "pred_masks": out_masks}

@@ -38,10 +38,10 @@ class ClipRunner:
 
     def run_device(self):
         """Inputs already resident in HBM (self.frames_dev); enqueues one clip on self.stream."""
-        if self.graph is not None:
-            self.graph.replay()
-        else:
-            with torch.cuda.stream(self.stream):
+        with torch.cuda.stream(self.stream):          # graph.replay() launches on the *current* stream
+            if self.graph is not None:
+                self.graph.replay()
+            else:
                 self.scores, self.masks = self._device_step()
 
     def run_host(self, frames_u8=None):

@@ -44,8 +44,8 @@ def fill_tensor(key, shape, seed=0, dtype=torch.float32):
             return uniform(0.8, 1.2)
         if "sampling_offsets" in key:            # pixel-scale offsets so samples spread over cells
             return randn(1.5)
-        if "class_embed" in key:
-            return randn(0.5, -2.0)
+        if "class_embed" in key:                 # prior-probability bias of the reference init (-4.6), jittered
+            return randn(0.5, -4.0)
         if is_norm:
             return randn(0.05)
         return randn(0.05)
