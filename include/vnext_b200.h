@@ -111,13 +111,39 @@ int vnext_msda_backward_host(int dtype, const void *value, const int64_t *spatia
  * the reference checkpoint stores it.  Replaces F.linear + separate bias/ReLU/residual/LayerNorm kernels of
  * projects/SeqFormer/seqformer/models/deformable_transformer.py:155-169 (forward_ffn, norm1/norm2) and
  * models/ops/modules/ms_deform_attn.py:94-100,114 (value/offset/weight/output projections).
- *   epilogue 0: + bias            1: relu(+ bias)
- *            2: LayerNorm(+ bias + residual[M, ldr]) * ln_gamma + ln_beta   (needs N == 256)
- * lda / ldo / ldr are row pitches in elements (multiples of 4); all pointers 16-byte aligned device memory.
+ *   flags: VNEXT_EPI_RELU | VNEXT_EPI_RESIDUAL (+ residual[M, ldr]) | VNEXT_EPI_LAYERNORM (over the N == 256
+ *          outputs of a row, after bias/residual; gamma, beta [N]); ReLU, when set, is applied last.
+ *   bias2d [bias_period, ldb2] (optional): geometry-dependent bias added as bias2d[row % bias_period][col] — used to
+ *          fold `(x + pos) W` into `x W + (pos W + b)` with the clip's position embedding projected once per layer.
+ *   row_mask [bias_period] (optional): rows with row_mask[row % bias_period] != 0 get columns [0, mask_cols) zeroed
+ *          (the reference's value.masked_fill(padding_mask, 0), ms_deform_attn.py:96-97).
+ * lda / ldo / ldr / ldb2 are row pitches in elements.  a, weight: 16-byte aligned, lda % 4 == 0, K % 4 == 0 (TMA).
  */
-int vnext_linear_tf32(const float *a, int lda, const float *weight, const float *bias, const float *residual,
-                      int ldr, const float *ln_gamma, const float *ln_beta, float ln_eps, float *out, int ldo,
-                      int M, int N, int K, int epilogue, void *stream);
+enum { VNEXT_EPI_RELU = 1, VNEXT_EPI_RESIDUAL = 2, VNEXT_EPI_LAYERNORM = 4 };
+int vnext_linear_tf32(const float *a, int lda, const float *weight, const float *bias, const float *bias2d,
+                      int bias_period, int ldb2, const unsigned char *row_mask, int mask_cols,
+                      const float *residual, int ldr, const float *ln_gamma, const float *ln_beta, float ln_eps,
+                      float *out, int ldo, int M, int N, int K, int flags, void *stream);
+
+/*
+ * Single-pass NHWC epilogues of the backbone / input projection (fp32, C % 4 == 0, 16-byte aligned):
+ *   vnext_bias_act      out = act(x + bias[c] (+ residual))      — folded FrozenBN bias + ReLU (+ shortcut) after a
+ *                       library conv (detectron2/modeling/backbone/resnet.py:194-210; layers/batch_norm.py:44-65)
+ *   vnext_stem_pool     out = maxpool3x3/s2/p1(relu(x + bias))    — BasicStem tail (resnet.py:355-359); x [N,H,W,C]
+ *   vnext_groupnorm_nhwc GroupNorm(groups, C == 8*groups) over x [N, HW, C], written to `out` with batch stride
+ *                       `out_batch_stride` elements (lets the caller place a level directly inside the [T, S, C]
+ *                       token tensor); stats_ws: 2*N*groups floats of scratch (deformable_detr.py:64-78)
+ *   vnext_preprocess    frames [T,3,H,W] (uint8 if in_is_u8 else fp32, 0..255) -> (x - mean)/std, zero padded to
+ *                       [T,Hp,Wp,3] channels-last (seqformer.py:413-429, util/misc.py:288-316); mean3/std3: HOST.
+ */
+int vnext_bias_act(const float *x, const float *bias, const float *residual, float *out, long long rows, int C,
+                   int relu, void *stream);
+int vnext_stem_pool(const float *x, const float *bias, float *out, int N, int H, int W, int C, void *stream);
+int vnext_groupnorm_nhwc(const float *x, const float *gamma, const float *beta, float *out,
+                         long long out_batch_stride, float *stats_ws, int N, int HW, int C, int groups, float eps,
+                         void *stream);
+int vnext_preprocess(int in_is_u8, const void *frames, float *out, int T, int H, int W, int Hp, int Wp,
+                     const float *mean3, const float *std3, void *stream);
 
 /* Which kernel variant the last forward / backward on this thread dispatched to
  * ("fwd_f32_d32_tma", "fwd_generic", ...).  For tests and profiles. */

@@ -1,0 +1,56 @@
+"""GPU numerics of the single-pass NHWC kernels vs plain PyTorch fp32 references of the same ops."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120)]
+
+
+def test_bias_act():
+    from vnext_b200 import fused
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(3, 17, 23, 64, generator=g).cuda()
+    b = torch.randn(64, generator=g).cuda()
+    r = torch.randn(3, 17, 23, 64, generator=g).cuda()
+    assert torch.equal(fused.bias_act(x, b, relu=True), F.relu(x + b))
+    assert torch.equal(fused.bias_act(x, b, relu=False, residual=r), x + b + r)
+    y = x.clone()
+    fused.bias_act(y, b, relu=True, residual=r, out=y)
+    assert torch.equal(y, F.relu(x + b + r))
+
+
+@pytest.mark.parametrize("H,W", [(368, 640), (7, 9), (48, 64)])
+def test_stem_pool(H, W):
+    from vnext_b200 import fused
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, H, W, 64, generator=g).cuda()
+    b = torch.randn(64, generator=g).cuda()
+    want = F.max_pool2d(F.relu(x.permute(0, 3, 1, 2) + b.view(1, -1, 1, 1)), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(fused.stem_pool(x, b), want.contiguous())
+
+
+@pytest.mark.parametrize("N,HW", [(5, 14720), (2, 12), (3, 240)])
+def test_groupnorm_nhwc_into_strided_output(N, HW):
+    from vnext_b200 import fused
+    g = torch.Generator().manual_seed(2)
+    x = (torch.randn(N, HW, 256, generator=g) * 3 + 1).cuda()
+    gamma, beta = (torch.rand(256, generator=g) + 0.5).cuda(), torch.randn(256, generator=g).cuda()
+    want = F.group_norm(x.double().permute(0, 2, 1), 32, gamma.double(), beta.double(), 1e-5).permute(0, 2, 1)
+    big = torch.zeros(N, HW + 100, 256, device="cuda")
+    fused.groupnorm_nhwc(x, gamma, beta, 32, 1e-5, out=big[:, 50:50 + HW, :])
+    assert (big[:, 50:50 + HW].double() - want).abs().max().item() < 1e-4
+    assert (big[:, :50] == 0).all() and (big[:, 50 + HW:] == 0).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.float32])
+def test_preprocess(dtype):
+    from vnext_b200 import fused
+    g = torch.Generator().manual_seed(3)
+    fr = torch.randint(0, 256, (3, 3, 80, 112), generator=g).to(dtype).cuda()
+    mean, std = (123.675, 116.280, 103.530), (58.395, 57.120, 57.375)
+    out = fused.preprocess(fr, mean, std, 96, 128)
+    m = torch.tensor(mean, device="cuda").view(1, 3, 1, 1)
+    s = torch.tensor(std, device="cuda").view(1, 3, 1, 1)
+    want = F.pad((fr.float() - m) / s, (0, 16, 0, 16)).permute(0, 2, 3, 1)
+    assert torch.allclose(out, want, rtol=1e-6, atol=1e-6)
+    assert (out[:, 80:] == 0).all() and (out[:, :, 112:] == 0).all()

@@ -57,3 +57,25 @@ def test_strided_views_and_errors():
         linear(x, torch.randn(384, 256, device="cuda"), torch.zeros(384, device="cuda"),
                residual=torch.zeros(256, 384, device="cuda"), ln_weight=torch.ones(384, device="cuda"),
                ln_bias=torch.zeros(384, device="cuda"))
+
+
+def test_residual_relu_bias2d_and_row_mask():
+    from vnext_b200.linear import linear
+    M, N, K, S = 1000, 384, 256, 250
+    x, w, b = _mk(M, N, K, 5)
+    g = torch.Generator().manual_seed(6)
+    res = torch.randn(M, N, generator=g).cuda()
+    b2 = torch.randn(S, N, generator=g).cuda()
+    mask = (torch.rand(S, generator=g) < 0.3).to(torch.uint8).cuda()
+    ref = F.linear(x.double(), w.double(), b.double())
+    tol = 2e-3 * ref.abs().max().item()
+    out = linear(x, w, b, relu=True, residual=res)
+    assert (out.double() - (ref + res.double()).clamp(min=0)).abs().max().item() < tol
+    out = linear(x, w, None, bias2d=b2)
+    want = F.linear(x.double(), w.double()) + b2.double().repeat(M // S, 1)
+    assert (out.double() - want).abs().max().item() < tol
+    out = linear(x, w, b, row_mask=mask, mask_cols=256)
+    want = ref.clone()
+    want[mask.bool().repeat(M // S).cpu().cuda(), :256] = 0
+    assert (out.double() - want).abs().max().item() < tol
+    assert (out[mask.bool().repeat(M // S), :256] == 0).all()

@@ -1,0 +1,220 @@
+// Memory-bound epilogue / normalisation kernels of the backbone and input projection (sm_100a), NHWC fp32.
+//
+// The reference runs these as separate ATen passes after each cuDNN conv (FrozenBN affine, ReLU, residual
+// add: detectron2/modeling/backbone/resnet.py:194-210,355-359, detectron2/layers/batch_norm.py:44-65;
+// max-pool resnet.py:358; GroupNorm(32) of input_proj: projects/SeqFormer/seqformer/models/
+// deformable_detr.py:64-78; pixel normalisation + /32 zero padding: seqformer.py:413-429, util/misc.py:288-316).
+// Here each is ONE pass over HBM with 16-byte accesses; grids are sized to the resident-CTA count and
+// grid-stride over the tensor.
+#include "common.cuh"
+
+namespace vnext {
+
+// out = act(x + bias[c] (+ residual))   rows x C, C % 4 == 0
+__global__ void __launch_bounds__(256) bias_act_kernel(const float4 *__restrict__ x, const float4 *__restrict__ bias,
+                                                       const float4 *__restrict__ residual, float4 *__restrict__ out,
+                                                       long long n4, int c4, int relu) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = x[i];
+        const float4 b = __ldg(bias + (int)(i % c4));
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        if (residual) {
+            const float4 r = residual[i];
+            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        }
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        out[i] = v;
+    }
+}
+
+// Stem tail: out[n, ho, wo, c] = max over the 3x3 / stride 2 / pad 1 window of relu(x + bias[c]).
+// relu and +bias are monotone, so this is relu(max(x) + bias): one read of the conv output, one quarter-size write.
+__global__ void __launch_bounds__(256) stem_pool_kernel(const float4 *__restrict__ x, const float4 *__restrict__ bias,
+                                                        float4 *__restrict__ out, int N, int H, int W, int Ho, int Wo,
+                                                        int c4) {
+    const long long total = (long long)N * Ho * Wo * c4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c4);
+        long long t = i / c4;
+        const int wo = (int)(t % Wo);
+        t /= Wo;
+        const int ho = (int)(t % Ho);
+        const int n = (int)(t / Ho);
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int h = 2 * ho - 1 + dy;
+            if (h < 0 || h >= H) continue;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const int w = 2 * wo - 1 + dx;
+                if (w < 0 || w >= W) continue;
+                const float4 v = x[((long long)(n * H + h) * W + w) * c4 + c];
+                m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+            }
+        }
+        const float4 b = __ldg(bias + c);
+        m.x = fmaxf(m.x + b.x, 0.f); m.y = fmaxf(m.y + b.y, 0.f); m.z = fmaxf(m.z + b.z, 0.f); m.w = fmaxf(m.w + b.w, 0.f);
+        out[i] = m;
+    }
+}
+
+// GroupNorm over [N, HW, C] (channels-last), G groups of C/G = 8 channels: statistics pass + apply pass.
+// stats[n][g] = (sum, sumsq) accumulated with one atomicAdd pair per (CTA, group).
+constexpr int kGnThreads = 256;
+__global__ void __launch_bounds__(kGnThreads) groupnorm_stats_kernel(const float4 *__restrict__ x, float *stats, int HW,
+                                                                     int C, int rows_per_cta) {
+    // thread -> (row offset, float4 column); C/4 float4 columns, two per 8-channel group
+    const int c4 = C / 4;
+    const int n = blockIdx.y;
+    const int col = threadIdx.x % c4, rsub = threadIdx.x / c4, rstep = kGnThreads / c4;
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int r1 = min(HW, r0 + rows_per_cta);
+    float s = 0.f, ss = 0.f;
+    for (int r = r0 + rsub; r < r1; r += rstep) {
+        const float4 v = x[((long long)n * HW + r) * c4 + col];
+        s += (v.x + v.y) + (v.z + v.w);
+        ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+    __shared__ float sh_s[kGnThreads], sh_ss[kGnThreads];
+    sh_s[threadIdx.x] = s;
+    sh_ss[threadIdx.x] = ss;
+    __syncthreads();
+    const int G = C / 8;
+    if (threadIdx.x < G) {      // group g owns float4 columns 2g and 2g+1 of every row-subset
+        float a = 0.f, b = 0.f;
+        for (int k = 0; k < rstep; ++k)
+            for (int h = 0; h < 2; ++h) {
+                a += sh_s[k * c4 + 2 * threadIdx.x + h];
+                b += sh_ss[k * c4 + 2 * threadIdx.x + h];
+            }
+        atomicAdd(stats + ((long long)n * G + threadIdx.x) * 2, a);
+        atomicAdd(stats + ((long long)n * G + threadIdx.x) * 2 + 1, b);
+    }
+}
+
+__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float4 *__restrict__ x, const float *__restrict__ stats,
+                                                              const float4 *__restrict__ gamma, const float4 *__restrict__ beta,
+                                                              float4 *__restrict__ out, int N, int HW, int C,
+                                                              long long out_batch_stride4, float eps) {
+    const int c4 = C / 4, G = C / 8;
+    const long long per = (long long)HW * c4;
+    const float inv_cnt = 1.f / (8.f * HW);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per * N; i += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(i / per);
+        const long long j = i % per;
+        const int col = (int)(j % c4);
+        const float *st = stats + ((long long)n * G + col / 2) * 2;
+        const float mean = st[0] * inv_cnt;
+        const float var = fmaxf(st[1] * inv_cnt - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + eps);
+        const float4 v = x[i], g = __ldg(gamma + col), b = __ldg(beta + col);
+        float4 o;
+        o.x = (v.x - mean) * rstd * g.x + b.x;
+        o.y = (v.y - mean) * rstd * g.y + b.y;
+        o.z = (v.z - mean) * rstd * g.z + b.z;
+        o.w = (v.w - mean) * rstd * g.w + b.w;
+        out[(long long)n * out_batch_stride4 + j] = o;
+    }
+}
+
+// uint8 / float frames [T, 3, H, W] (planar, 0..255) -> normalised, zero-padded channels-last [T, Hp, Wp, 3]
+template <typename T>
+__global__ void __launch_bounds__(256) preprocess_kernel(const T *__restrict__ in, float *__restrict__ out, int Tn, int H,
+                                                         int W, int Hp, int Wp, float m0, float m1, float m2, float s0,
+                                                         float s1, float s2) {
+    const long long total = (long long)Tn * Hp * Wp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(i % Wp);
+        const long long t2 = i / Wp;
+        const int h = (int)(t2 % Hp), t = (int)(t2 / Hp);
+        float r = 0.f, g = 0.f, b = 0.f;
+        if (h < H && w < W) {
+            const long long base = ((long long)t * 3 * H + h) * W + w;
+            r = ((float)in[base] - m0) / s0;
+            g = ((float)in[base + (long long)H * W] - m1) / s1;
+            b = ((float)in[base + 2ll * H * W] - m2) / s2;
+        }
+        out[i * 3] = r;
+        out[i * 3 + 1] = g;
+        out[i * 3 + 2] = b;
+    }
+}
+
+static inline int grid_for(long long work_items, int threads) {
+    long long b = (work_items + threads - 1) / threads;
+    const long long cap = (long long)num_sms() * 8;
+    return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace vnext
+
+using namespace vnext;
+
+extern "C" {
+
+int vnext_bias_act(const float *x, const float *bias, const float *residual, float *out, long long rows, int C, int relu,
+                   void *stream) {
+    VNEXT_CHECK_ARG(rows >= 0 && C > 0 && C % 4 == 0, "vnext_bias_act: C must be a positive multiple of 4 (got %d)", C);
+    if (rows == 0) return VNEXT_OK;
+    VNEXT_CHECK_ARG(x && bias && out, "vnext_bias_act: null pointer");
+    const long long n4 = rows * (C / 4);
+    bias_act_kernel<<<grid_for(n4, 256), 256, 0, (cudaStream_t)stream>>>((const float4 *)x, (const float4 *)bias,
+                                                                       (const float4 *)residual, (float4 *)out, n4, C / 4,
+                                                                       relu);
+    count_launch();
+    VNEXT_CUDA(cudaGetLastError());
+    return VNEXT_OK;
+}
+
+int vnext_stem_pool(const float *x, const float *bias, float *out, int N, int H, int W, int C, void *stream) {
+    VNEXT_CHECK_ARG(N >= 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "vnext_stem_pool: bad shape");
+    if (N == 0) return VNEXT_OK;
+    VNEXT_CHECK_ARG(x && bias && out, "vnext_stem_pool: null pointer");
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    const long long total = (long long)N * Ho * Wo * (C / 4);
+    stem_pool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const float4 *)x, (const float4 *)bias,
+                                                                           (float4 *)out, N, H, W, Ho, Wo, C / 4);
+    count_launch();
+    VNEXT_CUDA(cudaGetLastError());
+    return VNEXT_OK;
+}
+
+int vnext_groupnorm_nhwc(const float *x, const float *gamma, const float *beta, float *out, long long out_batch_stride,
+                         float *stats_ws, int N, int HW, int C, int groups, float eps, void *stream) {
+    VNEXT_CHECK_ARG(N >= 0 && HW > 0 && C > 0 && groups > 0 && C == groups * 8 && C <= 1024 && kGnThreads % (C / 4) == 0,
+                    "vnext_groupnorm_nhwc: supports C == 8*groups with C/4 dividing 256 (got C=%d groups=%d)", C, groups);
+    if (N == 0) return VNEXT_OK;
+    VNEXT_CHECK_ARG(x && gamma && beta && out && stats_ws && out_batch_stride % 4 == 0, "vnext_groupnorm_nhwc: bad pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    VNEXT_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * N * groups, st));
+    const int rows_per_cta = 64;
+    dim3 grid((HW + rows_per_cta - 1) / rows_per_cta, N);
+    groupnorm_stats_kernel<<<grid, kGnThreads, 0, st>>>((const float4 *)x, stats_ws, HW, C, rows_per_cta);
+    const long long total = (long long)N * HW * (C / 4);
+    groupnorm_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>((const float4 *)x, stats_ws, (const float4 *)gamma,
+                                                               (const float4 *)beta, (float4 *)out, N, HW, C,
+                                                               out_batch_stride / 4, eps);
+    count_launch(3);
+    VNEXT_CUDA(cudaGetLastError());
+    return VNEXT_OK;
+}
+
+int vnext_preprocess(int in_is_u8, const void *frames, float *out, int T, int H, int W, int Hp, int Wp, const float *mean3,
+                     const float *std3, void *stream) {
+    VNEXT_CHECK_ARG(T >= 0 && H > 0 && W > 0 && Hp >= H && Wp >= W, "vnext_preprocess: bad shape");
+    if (T == 0) return VNEXT_OK;
+    VNEXT_CHECK_ARG(frames && out && mean3 && std3, "vnext_preprocess: null pointer");
+    const long long total = (long long)T * Hp * Wp;
+    if (in_is_u8)
+        preprocess_kernel<unsigned char><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+            (const unsigned char *)frames, out, T, H, W, Hp, Wp, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]);
+    else
+        preprocess_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+            (const float *)frames, out, T, H, W, Hp, Wp, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]);
+    count_launch();
+    VNEXT_CUDA(cudaGetLastError());
+    return VNEXT_OK;
+}
+
+}  // extern "C"

@@ -104,23 +104,67 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-enum { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_BIAS_RES_LN = 2 };
+enum { EPI_RELU = 1, EPI_RESIDUAL = 2, EPI_LAYERNORM = 4 };
 
 struct GemmParams {
     int M, N, K;
     const float *bias;       // [N] or null
-    const float *residual;   // [M, ldr] (EPI_BIAS_RES_LN)
-    const float *gamma;      // [N]
+    const float *bias2d;     // [period, ldb2] or null: added as bias2d[row % period][col] (geometry-dependent bias)
+    int period, ldb2;
+    const unsigned char *row_mask;   // [period] or null: rows with mask != 0 get columns [0, mask_cols) zeroed
+    int mask_cols;
+    const float *residual;   // [M, ldr] (EPI_RESIDUAL)
+    const float *gamma;      // [N]      (EPI_LAYERNORM)
     const float *beta;       // [N]
     float *out;              // [M, ldo]
     int ldo, ldr;
-    int mode;
+    int flags;
+    int vec_ok;              // out / residual / bias rows allow 16-byte vector access
     float eps;
     int num_m_tiles, num_n_tiles;
 };
 
 constexpr int kGemmThreads = 256;
 constexpr int BLOCK_M = 128;
+
+// x[j] = acc + bias + bias2d + residual for 32 consecutive columns starting at global column `col0` of `row`
+__device__ __forceinline__ void epilogue_add(const GemmParams &p, int row, bool row_ok, int col0, uint32_t (&v)[32]) {
+    const bool vec = p.vec_ok && (col0 + 32 <= p.N);
+    const float *b2 = p.bias2d ? p.bias2d + (size_t)(row % p.period) * p.ldb2 + col0 : nullptr;
+    const float *rr = (p.flags & EPI_RESIDUAL) ? p.residual + (size_t)row * p.ldr + col0 : nullptr;
+    if (vec) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            float4 x = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                   __uint_as_float(v[j + 3]));
+            if (p.bias) {
+                const float4 b = *reinterpret_cast<const float4 *>(p.bias + col0 + j);
+                x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+            }
+            if (b2 && row_ok) {
+                const float4 b = *reinterpret_cast<const float4 *>(b2 + j);
+                x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+            }
+            if (rr && row_ok) {
+                const float4 r = *reinterpret_cast<const float4 *>(rr + j);
+                x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
+            }
+            v[j] = __float_as_uint(x.x); v[j + 1] = __float_as_uint(x.y);
+            v[j + 2] = __float_as_uint(x.z); v[j + 3] = __float_as_uint(x.w);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]);
+            if (col0 + j < p.N) {
+                if (p.bias) x += p.bias[col0 + j];
+                if (b2 && row_ok) x += b2[j];
+                if (rr && row_ok) x += rr[j];
+            }
+            v[j] = __float_as_uint(x);
+        }
+    }
+}
 
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -208,6 +252,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // ===================== epilogue =====================
         const int ew = warp - 4;                                   // TMEM lane quarter this warp may touch
         int acc = 0, acc_phase = 0;
+        const bool relu = (p.flags & EPI_RELU) != 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_idx = (tile / p.num_n_tiles) * BLOCK_M, n_idx = (tile % p.num_n_tiles) * BLOCK_N;
             mbar_wait(&tmem_full[acc], acc_phase);
@@ -215,27 +260,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int row = m_idx + ew * 32 + lane;
             const bool row_ok = row < p.M;
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
-            float *orow = p.out + (size_t)row * p.ldo + n_idx;
-            if (p.mode == EPI_BIAS_RES_LN) {
-                // pass 1: x = acc + bias + residual, parked back in TMEM; thread-local mean / variance
-                const float *rrow = p.residual + (size_t)row * p.ldr + n_idx;
+            float *orow = p.out + (size_t)row * p.ldo;
+            const bool masked = p.row_mask && row_ok && p.row_mask[row % p.period] != 0;
+            if (p.flags & EPI_LAYERNORM) {
+                // pass 1: x = acc + bias (+ residual), parked back in TMEM; thread-local mean / variance (lane == row)
                 float sum = 0.f, sumsq = 0.f;
 #pragma unroll 1
                 for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld32(taddr + c0, v);
                     tmem_ld_wait();
+                    epilogue_add(p, row, row_ok, n_idx + c0, v);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (row_ok) r = *reinterpret_cast<const float4 *>(rrow + c0 + j);
-                        const float4 b = *reinterpret_cast<const float4 *>(p.bias + n_idx + c0 + j);
-                        float x0 = __uint_as_float(v[j]) + b.x + r.x, x1 = __uint_as_float(v[j + 1]) + b.y + r.y;
-                        float x2 = __uint_as_float(v[j + 2]) + b.z + r.z, x3 = __uint_as_float(v[j + 3]) + b.w + r.w;
-                        sum += (x0 + x1) + (x2 + x3);
-                        sumsq += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
-                        v[j] = __float_as_uint(x0); v[j + 1] = __float_as_uint(x1);
-                        v[j + 2] = __float_as_uint(x2); v[j + 3] = __float_as_uint(x3);
+                    for (int j = 0; j < 32; ++j) {
+                        const float x = __uint_as_float(v[j]);
+                        sum += x;
+                        sumsq = fmaf(x, x, sumsq);
                     }
                     tmem_st32(taddr + c0, v);
                 }
@@ -258,38 +298,39 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             o.y = (__uint_as_float(v[j + 1]) - mean) * rstd * g.y + be.y;
                             o.z = (__uint_as_float(v[j + 2]) - mean) * rstd * g.z + be.z;
                             o.w = (__uint_as_float(v[j + 3]) - mean) * rstd * g.w + be.w;
-                            *reinterpret_cast<float4 *>(orow + c0 + j) = o;
+                            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                            *reinterpret_cast<float4 *>(orow + n_idx + c0 + j) = o;
                         }
                     }
                 }
             } else {
-                const bool relu = p.mode == EPI_BIAS_RELU;
 #pragma unroll 1
                 for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                    if (n_idx + c0 >= p.N) break;                  // warp-uniform
                     uint32_t v[32];
                     tmem_ld32(taddr + c0, v);
                     tmem_ld_wait();
+                    epilogue_add(p, row, row_ok, n_idx + c0, v);
                     if (row_ok) {
+                        const int col0 = n_idx + c0;
+                        if (p.vec_ok && col0 + 32 <= p.N) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const int col = n_idx + c0 + j;
-                            if (col + 3 < p.N) {
-                                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (p.bias) b = *reinterpret_cast<const float4 *>(p.bias + col);
-                                float4 o = make_float4(__uint_as_float(v[j]) + b.x, __uint_as_float(v[j + 1]) + b.y,
-                                                       __uint_as_float(v[j + 2]) + b.z, __uint_as_float(v[j + 3]) + b.w);
-                                if (relu) {
-                                    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                                }
-                                *reinterpret_cast<float4 *>(orow + c0 + j) = o;
-                            } else {
-#pragma unroll
-                                for (int t = 0; t < 4; ++t)
-                                    if (col + t < p.N) {
-                                        float o = __uint_as_float(v[j + t]) + (p.bias ? p.bias[col + t] : 0.f);
-                                        orow[c0 + j + t] = relu ? fmaxf(o, 0.f) : o;
-                                    }
+                            for (int j = 0; j < 32; j += 4) {
+                                float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                       __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                                if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                                if (masked && col0 + j < p.mask_cols) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                                *reinterpret_cast<float4 *>(orow + col0 + j) = o;
                             }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < p.N) {
+                                    float o = __uint_as_float(v[j]);
+                                    if (relu) o = fmaxf(o, 0.f);
+                                    if (masked && col0 + j < p.mask_cols) o = 0.f;
+                                    orow[col0 + j] = o;
+                                }
                         }
                     }
                 }
@@ -366,22 +407,40 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, GemmParams 
     return VNEXT_OK;
 }
 
-int linear_tf32_device(const float *a, int lda, const float *w, const float *bias, const float *residual, int ldr,
-                       const float *gamma, const float *beta, float eps, float *out, int ldo, int M, int N, int K,
-                       int mode, cudaStream_t stream) {
-    if (M == 0 || N == 0) return VNEXT_OK;
+struct LinearArgs {
+    const float *a; int lda;
+    const float *w;
+    const float *bias;
+    const float *bias2d; int period, ldb2;
+    const unsigned char *row_mask; int mask_cols;
+    const float *residual; int ldr;
+    const float *gamma, *beta; float eps;
+    float *out; int ldo;
+    int M, N, K, flags;
+};
+
+static inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int linear_tf32_device(const LinearArgs &x, cudaStream_t stream) {
+    if (x.M == 0 || x.N == 0) return VNEXT_OK;
     GemmParams p;
-    p.M = M; p.N = N; p.K = K; p.bias = bias; p.residual = residual; p.gamma = gamma; p.beta = beta; p.out = out;
-    p.ldo = ldo; p.ldr = ldr; p.mode = mode; p.eps = eps; p.num_m_tiles = p.num_n_tiles = 0;
-    const bool wide = (N % 256 == 0);
-    if (mode == EPI_BIAS_RES_LN && N != 256) {
-        set_error("vnext_linear: the fused residual+LayerNorm epilogue needs N == 256 (got %d)", N);
-        return VNEXT_EINVAL;
+    p.M = x.M; p.N = x.N; p.K = x.K; p.bias = x.bias; p.bias2d = x.bias2d; p.period = x.period > 0 ? x.period : 1;
+    p.ldb2 = x.ldb2; p.row_mask = x.row_mask; p.mask_cols = x.mask_cols; p.residual = x.residual; p.gamma = x.gamma;
+    p.beta = x.beta; p.out = x.out; p.ldo = x.ldo; p.ldr = x.ldr; p.flags = x.flags; p.eps = x.eps;
+    p.num_m_tiles = p.num_n_tiles = 0;
+    p.vec_ok = al16(x.out) && x.ldo % 4 == 0 && (!x.bias || al16(x.bias)) &&
+               (!x.bias2d || (al16(x.bias2d) && x.ldb2 % 4 == 0)) && (!x.residual || (al16(x.residual) && x.ldr % 4 == 0));
+    const bool wide = (x.N % 256 == 0);
+    if (x.flags & EPI_LAYERNORM) {
+        if (x.N != 256 || !p.vec_ok || !x.gamma || !x.beta || !al16(x.gamma) || !al16(x.beta)) {
+            set_error("vnext_linear: the fused LayerNorm epilogue needs N == 256 (got %d) and 16-B aligned operands", x.N);
+            return VNEXT_EINVAL;
+        }
     }
     CUtensorMap ta, tb;
-    int rc = make_tmap_f32(&ta, a, M, K, lda, BLOCK_M);
+    int rc = make_tmap_f32(&ta, x.a, x.M, x.K, x.lda, BLOCK_M);
     if (rc) return rc;
-    rc = make_tmap_f32(&tb, w, N, K, K, wide ? 256 : 128);
+    rc = make_tmap_f32(&tb, x.w, x.N, x.K, x.K, wide ? 256 : 128);
     if (rc) return rc;
     return wide ? launch_gemm<256, 4>(ta, tb, p, stream) : launch_gemm<128, 6>(ta, tb, p, stream);
 }
@@ -390,21 +449,20 @@ int linear_tf32_device(const float *a, int lda, const float *w, const float *bia
 
 using namespace vnext;
 
-extern "C" int vnext_linear_tf32(const float *a, int lda, const float *weight, const float *bias, const float *residual,
-                                 int ldr, const float *ln_gamma, const float *ln_beta, float ln_eps, float *out,
-                                 int ldo, int M, int N, int K, int epilogue, void *stream) {
+extern "C" int vnext_linear_tf32(const float *a, int lda, const float *weight, const float *bias, const float *bias2d,
+                                 int bias_period, int ldb2, const unsigned char *row_mask, int mask_cols,
+                                 const float *residual, int ldr, const float *ln_gamma, const float *ln_beta,
+                                 float ln_eps, float *out, int ldo, int M, int N, int K, int flags, void *stream) {
     VNEXT_CHECK_ARG(M >= 0 && N >= 0 && K > 0, "vnext_linear_tf32: bad sizes M=%d N=%d K=%d", M, N, K);
-    VNEXT_CHECK_ARG(epilogue >= 0 && epilogue <= 2, "vnext_linear_tf32: unknown epilogue %d", epilogue);
+    VNEXT_CHECK_ARG(flags >= 0 && flags < 8, "vnext_linear_tf32: unknown epilogue flags %d", flags);
     if (M == 0 || N == 0) return VNEXT_OK;
     VNEXT_CHECK_ARG(a && weight && out, "vnext_linear_tf32: null pointer");
-    VNEXT_CHECK_ARG((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(weight) & 15) == 0 &&
-                        (reinterpret_cast<uintptr_t>(out) & 15) == 0 && lda % 4 == 0 && K % 4 == 0 && ldo % 4 == 0,
-                    "vnext_linear_tf32: pointers must be 16-byte aligned and lda, K, ldo multiples of 4");
-    VNEXT_CHECK_ARG(!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "vnext_linear_tf32: bias must be 16-B aligned");
-    if (epilogue == EPI_BIAS_RES_LN)
-        VNEXT_CHECK_ARG(bias && residual && ln_gamma && ln_beta && ldr % 4 == 0 &&
-                            (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
-                        "vnext_linear_tf32: residual+LayerNorm epilogue needs bias, residual, gamma, beta (16-B aligned)");
-    return linear_tf32_device(a, lda, weight, bias, residual, ldr, ln_gamma, ln_beta, ln_eps, out, ldo, M, N, K, epilogue,
-                              static_cast<cudaStream_t>(stream));
+    VNEXT_CHECK_ARG(al16(a) && al16(weight) && lda % 4 == 0 && K % 4 == 0,
+                    "vnext_linear_tf32: a / weight must be 16-byte aligned with lda and K multiples of 4 (TMA)");
+    VNEXT_CHECK_ARG(!(flags & EPI_RESIDUAL) || residual, "vnext_linear_tf32: residual flag without residual pointer");
+    VNEXT_CHECK_ARG(!bias2d || bias_period > 0, "vnext_linear_tf32: bias2d needs a positive period");
+    VNEXT_CHECK_ARG(!row_mask || bias_period > 0, "vnext_linear_tf32: row_mask needs a positive period");
+    LinearArgs x{a, lda, weight, bias, bias2d, bias_period, ldb2, row_mask, mask_cols, residual, ldr,
+                 ln_gamma, ln_beta, ln_eps, out, ldo, M, N, K, flags};
+    return linear_tf32_device(x, static_cast<cudaStream_t>(stream));
 }

@@ -86,6 +86,10 @@ class SeqFormerEngine:
         self.mask_stride = mask_stride
         self.precision = precision
         self._msda_impl = msda_impl
+        # native = hand-written CUDA kernels for the projections / epilogues / norms as well as the sampler;
+        # the plain-torch formulation below each `if self.native` is the same math and is what the CPU unit
+        # tests of the host logic exercise (with an injected sampler).
+        self.native = (self.device.type == "cuda") and msda_impl is None
         self._plans: Dict[Tuple[int, int, int], ClipPlan] = {}
         sd = state_dict
         dev = self.device
@@ -94,6 +98,7 @@ class SeqFormerEngine:
         self.num_queries = sd[DETR + "query_embed.weight"].shape[0]
         self.pixel_mean = torch.tensor(pixel_mean, device=dev).view(1, 3, 1, 1)
         self.pixel_std = torch.tensor(pixel_std, device=dev).view(1, 3, 1, 1)
+        self._mean3, self._std3 = tuple(pixel_mean), tuple(pixel_std)
 
         def cl(w):   # conv weights in channels-last
             return f32(w).contiguous(memory_format=torch.channels_last)
@@ -188,6 +193,16 @@ class SeqFormerEngine:
             acc += hh * ww
         plan.extra["lsi_list"] = starts                          # python ints: no device sync in the forward
         plan.extra["scale_wh"] = torch.tensor([float(W), float(H)], device=dev)
+        plan.extra["mask_u8"] = plan.mask_flat[0].to(torch.uint8).contiguous()
+        if self.native:
+            # (x + pos) W_oa + b  ==  x W_oa + (pos W_oa + b): the clip geometry's share of the offset/attention
+            # projection, once per layer per plan (exact fp32), consumed as a row-periodic bias by the GEMM epilogue
+            prev = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = False
+            plan.extra["enc_posproj"] = [F.linear(plan.pos_flat[0], w["attn"]["oa_w"], w["attn"]["oa_b"]).contiguous()
+                                         for w in self.enc]
+            torch.backends.cuda.matmul.allow_tf32 = prev
+            plan.extra["gn_ws"] = torch.empty(2 * T * 32, dtype=torch.float32, device=dev)
         self._plans[key] = plan
         return plan
 
@@ -225,13 +240,28 @@ class SeqFormerEngine:
     def _lin(x, wb):
         return F.linear(x, wb[0], wb[1])
 
-    def _mha(self, q_in, v_in, w):
-        """nn.MultiheadAttention(q=k=q_in, v=v_in), batch-first [B, n, C]."""
+    def lin(self, x, wb, relu=False, residual=None, ln=None, **kw):
+        """y = [relu]( [LayerNorm]( x W^T + b [+ residual] ) ) — one tcgen05 kernel when native."""
+        if self.native:
+            from ..linear import linear
+            if residual is not None and residual.shape != x.shape[:-1] + (wb[0].shape[0],):
+                residual = residual.expand(*x.shape[:-1], wb[0].shape[0])
+            return linear(x, wb[0], wb[1], relu=relu, residual=residual, ln_weight=None if ln is None else ln[0],
+                          ln_bias=None if ln is None else ln[1], **kw)
+        y = F.linear(x, wb[0], wb[1])
+        if residual is not None:
+            y = y + residual
+        if ln is not None:
+            y = F.layer_norm(y, (y.shape[-1],), ln[0], ln[1], 1e-5)
+        return F.relu(y) if relu else y
+
+    def _mha(self, q_in, v_in, w, residual=None, ln=None):
+        """LN(residual + nn.MultiheadAttention(q=k=q_in, v=v_in)), batch-first [B, n, C]."""
         in_w, in_b, out_w, out_b = w
         C, H = self.C, self.M
         B, n, _ = q_in.shape
-        qk = F.linear(q_in, in_w[:2 * C], in_b[:2 * C])
-        v = F.linear(v_in, in_w[2 * C:], in_b[2 * C:])
+        qk = self.lin(q_in, (in_w[:2 * C], in_b[:2 * C]))
+        v = self.lin(v_in, (in_w[2 * C:], in_b[2 * C:]))
         q, k = qk[..., :C], qk[..., C:]
         d = C // H
         q = q.reshape(B, n, H, d).transpose(1, 2) * (d ** -0.5)
@@ -239,17 +269,69 @@ class SeqFormerEngine:
         v = v.reshape(B, n, H, d).transpose(1, 2)
         a = torch.softmax(q @ k.transpose(-1, -2), dim=-1)
         o = (a @ v).transpose(1, 2).reshape(B, n, C)
-        return F.linear(o, out_w, out_b)
+        return self.lin(o, (out_w, out_b), residual=residual, ln=ln)
 
     # ------------------------------------------------------------------ stages
     def preprocess(self, frames, plan):
-        """frames [T,3,H,W] float (0..255) on device -> normalised, zero-padded channels-last [T,3,Hp,Wp]."""
-        x = (frames - self.pixel_mean) / self.pixel_std
+        """frames [T,3,H,W] uint8/float (0..255) on device -> normalised, zero-padded channels-last [T,3,Hp,Wp]."""
+        if self.native:
+            from .. import fused
+            x = fused.preprocess(frames.contiguous(), self._mean3, self._std3, plan.Hp, plan.Wp)
+            return x.permute(0, 3, 1, 2)                  # logical NCHW over NHWC memory (= channels_last)
+        x = (frames.float() - self.pixel_mean) / self.pixel_std
         if plan.any_pad:
             x = F.pad(x, (0, plan.Wp - plan.W, 0, plan.Hp - plan.H))
         return x.contiguous(memory_format=torch.channels_last)
 
+    def _conv3x3_native(self, x_nhwc, wb, stride=1, relu=True):
+        """3x3 conv on the library (cuDNN, no bias) + ONE fused bias/ReLU pass.  x_nhwc: [T,h,w,C] contiguous."""
+        from .. import fused
+        y = F.conv2d(x_nhwc.permute(0, 3, 1, 2), wb[0], None, stride=stride, padding=1).permute(0, 2, 3, 1)
+        return fused.bias_act(y, wb[1], relu=relu, out=y)
+
+    def backbone_native(self, x):
+        """NHWC throughout; 1x1 convs are tcgen05 GEMMs with fused bias/ReLU/residual epilogues."""
+        from .. import fused
+        y = F.conv2d(x, self.stem[0], None, stride=2, padding=3).permute(0, 2, 3, 1)
+        x = fused.stem_pool(y, self.stem[1])                                   # [T, H/4, W/4, 64]
+        feats = {}
+        for name, blocks in self.stages:
+            for blk in blocks:
+                s = blk["stride"]
+                y = self.lin(x, self._w2d(blk["conv1"]), relu=True)
+                y = self._conv3x3_native(y, blk["conv2"], stride=s)
+                if blk["shortcut"] is None:
+                    sc = x
+                else:
+                    xs = x if s == 1 else x[:, ::s, ::s, :].contiguous()
+                    sc = self.lin(xs, self._w2d(blk["shortcut"]))
+                x = self.lin(y, self._w2d(blk["conv3"]), relu=True, residual=sc)
+            feats[name] = x
+        return feats
+
+    @staticmethod
+    def _w2d(wb):
+        return (wb[0].reshape(wb[0].shape[0], -1), wb[1])
+
+    def tokens_native(self, feats, plan):
+        from .. import fused
+        T = plan.T
+        X = torch.empty((T, plan.S, self.C), dtype=torch.float32, device=self.device)
+        for l, name in enumerate(("res3", "res4", "res5", "res5")):
+            w, b, gw, gb = self.input_proj[l]
+            h, wd = plan.level_hw[l]
+            if l < 3:
+                y = self.lin(feats[name], (w.reshape(self.C, -1), b)).reshape(T, h * wd, self.C)
+            else:
+                y = F.conv2d(feats[name].permute(0, 3, 1, 2), w, b, stride=2, padding=1).permute(0, 2, 3, 1)
+                y = y.reshape(T, h * wd, self.C)
+            s0 = plan.extra["lsi_list"][l]
+            fused.groupnorm_nhwc(y, gw, gb, 32, 1e-5, out=X[:, s0:s0 + h * wd, :], stats_ws=plan.extra["gn_ws"])
+        return X
+
     def backbone(self, x):
+        if self.native:
+            return self.backbone_native(x)
         x = self._conv(x, self.stem, stride=2, padding=3, relu=True)
         x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
         feats = {}
@@ -264,6 +346,8 @@ class SeqFormerEngine:
         return feats
 
     def tokens(self, feats, plan):
+        if self.native:
+            return self.tokens_native(feats, plan)
         toks = []
         for l, name in enumerate(("res3", "res4", "res5", "res5")):
             w, b, gw, gb = self.input_proj[l]
@@ -273,18 +357,25 @@ class SeqFormerEngine:
         return torch.cat(toks, 1)                      # [T, S, C]
 
     def _value(self, x, attn_w, plan):
-        v = F.linear(x, attn_w["v_w"], attn_w["v_b"])
-        if plan.any_pad:
-            v = v.masked_fill(plan.mask_flat[..., None], 0.0)
+        if self.native:      # padding rows zeroed in the GEMM epilogue
+            kw = {"row_mask": plan.extra["mask_u8"], "mask_cols": self.C} if plan.any_pad else {}
+            v = self.lin(x, (attn_w["v_w"], attn_w["v_b"]), **kw)
+        else:
+            v = F.linear(x, attn_w["v_w"], attn_w["v_b"])
+            if plan.any_pad:
+                v = v.masked_fill(plan.mask_flat[..., None], 0.0)
         return v.view(x.shape[0], x.shape[1], self.M, self.C // self.M)
 
     def encoder(self, x, plan):
-        for w in self.enc:
+        for i, w in enumerate(self.enc):
             a = w["attn"]
-            oa = F.linear(x + plan.pos_flat, a["oa_w"], a["oa_b"])
+            if self.native:
+                oa = self.lin(x, (a["oa_w"], None), bias2d=plan.extra["enc_posproj"][i])
+            else:
+                oa = F.linear(x + plan.pos_flat, a["oa_w"], a["oa_b"])
             s = self.sample(self._value(x, a, plan), oa, plan.enc_ref, plan, a["n_off"])
-            x = self._ln(x + F.linear(s, a["o_w"], a["o_b"]), w["norm1"])
-            x = self._ln(x + self._lin(F.relu(self._lin(x, w["lin1"])), w["lin2"]), w["norm2"])
+            x = self.lin(s, (a["o_w"], a["o_b"]), residual=x, ln=w["norm1"])
+            x = self.lin(self.lin(x, w["lin1"], relu=True), w["lin2"], residual=x, ln=w["norm2"])
         return x
 
     def decoder(self, memory, plan, collect_all=False):
@@ -301,25 +392,23 @@ class SeqFormerEngine:
             else:
                 ref_in = ref[:, :, None] * vr[:, None]
             q = out + qpos
-            out = self._ln(out + self._mha(q, out, w["self_attn"]), w["norm2"])
+            out = self._mha(q, out, w["self_attn"], residual=out, ln=w["norm2"])
             qb = out_box + qpos
-            out_box = self._ln(out_box + self._mha(qb, out_box, w["self_attn_box"]), w["norm2_box"])
+            out_box = self._mha(qb, out_box, w["self_attn_box"], residual=out_box, ln=w["norm2_box"])
             a = w["attn"]
-            oa = F.linear(out_box + qpos, a["oa_w"], a["oa_b"]).expand(T, -1, -1)
+            oa = self.lin(out_box + qpos, (a["oa_w"], a["oa_b"])).expand(T, -1, -1)
             s = self.sample(self._value(memory, a, plan), oa, ref_in, plan, a["n_off"])      # [T, nq, C]
-            t2b = F.linear(s, a["ob_w"], a["ob_b"])
-            t2, t2_box = t2b[..., :C], t2b[..., C:]
-            out_box = self._ln(out_box + t2_box, w["norm1_box"])                               # broadcasts to [T, nq, C]
-            out_box = self._ln(out_box + self._lin(F.relu(self._lin(out_box, w["linear1_box"])), w["linear2_box"]),
-                               w["norm3_box"])
-            tw = torch.softmax(self._lin(out_box, w["time_attention_weights"]), 0)
+            t2 = self.lin(s, (a["o_w"], a["o_b"]))
+            # tgt_box = norm1_box(tgt_box + output_proj_box(sampled)); broadcasts [1,nq,C] -> [T,nq,C] in layer 0
+            out_box = self.lin(s, (a["ob_w"][C:], a["ob_b"][C:]), residual=out_box.expand(T, -1, -1), ln=w["norm1_box"])
+            out_box = self.lin(self.lin(out_box, w["linear1_box"], relu=True), w["linear2_box"], residual=out_box,
+                               ln=w["norm3_box"])
+            tw = torch.softmax(self.lin(out_box, w["time_attention_weights"]), 0)
             out = self._ln(out + (t2 * tw).sum(0, keepdim=True), w["norm1"])
-            out = self._ln(out + self._lin(F.relu(self._lin(out, w["linear1"])), w["linear2"]), w["norm3"])
+            out = self.lin(self.lin(out, w["linear1"], relu=True), w["linear2"], residual=out, ln=w["norm3"])
             tmp = out_box
             for j, wb in enumerate(w["bbox"]):
-                tmp = self._lin(tmp, wb)
-                if j < 2:
-                    tmp = F.relu(tmp)
+                tmp = self.lin(tmp, wb, relu=(j < 2))
             prev_ref = ref
             if ref.shape[-1] == 4:
                 ref = (tmp + inverse_sigmoid(ref)).sigmoid()
@@ -334,12 +423,10 @@ class SeqFormerEngine:
         lid, hs, hs_box, prev_ref = level
         w = self.dec[lid]
         reference = inverse_sigmoid(prev_ref)                    # [T, nq, 2|4]
-        logits = self._lin(hs, w["cls"])                         # [1, nq, K]
+        logits = self.lin(hs, w["cls"])                          # [1, nq, K]
         tmp = hs_box
         for j, wb in enumerate(w["bbox"]):
-            tmp = self._lin(tmp, wb)
-            if j < 2:
-                tmp = F.relu(tmp)
+            tmp = self.lin(tmp, wb, relu=(j < 2))
         if reference.shape[-1] == 4:
             tmp = tmp + reference
         else:
@@ -347,9 +434,7 @@ class SeqFormerEngine:
         boxes = tmp.sigmoid()                                    # [T, nq, 4]
         params = hs
         for j, wb in enumerate(self.controller):
-            params = self._lin(params, wb)
-            if j < 2:
-                params = F.relu(params)
+            params = self.lin(params, wb, relu=(j < 2))
         ref_px = reference[..., :2].sigmoid() * plan.extra["scale_wh"]   # [T, nq, 2] in pixels
         return logits, boxes, params[0], ref_px
 
@@ -362,6 +447,15 @@ class SeqFormerEngine:
             s0 = plan.extra["lsi_list"][l]
             lv.append(memory[:, s0:s0 + h * w, :].reshape(T, h, w, C).permute(0, 3, 1, 2))
         mh = self.mask_head
+        if self.native:
+            nh = [t.permute(0, 2, 3, 1) for t in lv]                     # NHWC views of the memory levels
+            c3 = self._conv3x3_native
+            x = c3(nh[2], mh["lay3"]).permute(0, 3, 1, 2)
+            x = (nh[1] + F.interpolate(x, size=lv[1].shape[-2:], mode="nearest").permute(0, 2, 3, 1))
+            x = c3(x, mh["lay4"]).permute(0, 3, 1, 2)
+            x = (nh[0] + F.interpolate(x, size=lv[0].shape[-2:], mode="nearest").permute(0, 2, 3, 1))
+            x = c3(c3(c3(x, mh["dcn"]), mh["lay1"]), mh["lay2"])
+            return x.permute(0, 3, 1, 2)
         x = self._conv(lv[2], mh["lay3"], padding=1, relu=True)
         x = lv[1] + F.interpolate(x, size=lv[1].shape[-2:], mode="nearest")
         x = self._conv(x, mh["lay4"], padding=1, relu=True)

@@ -34,7 +34,7 @@ class ClipRunner:
         self.d2h_bytes = self.scores_pin.numel() * 4 + self.masks_pin.numel()
 
     def _device_step(self):
-        return self.engine.infer_video_device(self.frames_dev.float(), self.ori_size, self.topk)
+        return self.engine.infer_video_device(self.frames_dev, self.ori_size, self.topk)   # uint8 in, fused normalise
 
     def run_device(self):
         """Inputs already resident in HBM (self.frames_dev); enqueues one clip on self.stream."""
