@@ -70,6 +70,24 @@ int vnext_msda_forward(int dtype, const void *value, const int64_t *spatial_shap
                        void *stream);
 
 /*
+ * Forward with the module's pre-ops fused in (softmax over L*K, sampling-location arithmetic), replacing the
+ * ATen passes of MSDeformAttn.forward around the op (ops/modules/ms_deform_attn.py:98-108; SeqFormer variant
+ * S/models/ops/modules/ms_deform_attn.py:98-121, 140-176):
+ *   offsets_logits  fp32 [batch*num_query, row_pitch]: per row M*L*K*2 raw sampling offsets (head, level, point, xy)
+ *                   followed by M*L*K raw attention logits — i.e. the concatenated sampling_offsets /
+ *                   attention_weights projections of the query
+ *   reference_points fp32 [ref_shared ? 1 : batch, num_query, num_levels, ref_dim], ref_dim 2 (x, y) or 4 (x, y, w, h)
+ *   loc = ref_xy + off / (W_l, H_l)            (ref_dim 2)      loc = ref_xy + off / num_point * ref_wh * 0.5  (ref_dim 4)
+ *   attn = softmax over the L*K logits of each (query, head);   output as vnext_msda_forward.
+ * Tile kernels only: channels == 32, num_levels*num_point in {4, 8, 16, 32}, value fp32 or bf16.
+ */
+int vnext_msda_forward_fused(int dtype, const void *value, const int64_t *spatial_shapes,
+                             const int64_t *level_start_index, const float *offsets_logits, int row_pitch,
+                             const float *reference_points, int ref_dim, int ref_shared, int batch, int spatial_size,
+                             int num_heads, int channels, int num_levels, int num_query, int num_point, void *output,
+                             void *stream);
+
+/*
  * Backward.  grad_output [batch, num_query, num_heads*channels] (dtype).
  * Outputs are fully (over)written: grad_value like value (zero-filled then accumulated with
  * atomics, as the reference), grad_sampling_loc like sampling_loc, grad_attn_weight like attn_weight.

@@ -259,3 +259,38 @@ def test_host_buffer_cabi(ops):
     cv, cl, ca = O.backward_c(value, shapes, lsi, loc, attn, torch.from_numpy(gout), np.float64)
     assert torch.allclose(torch.from_numpy(gv).double(), cv, rtol=1e-3, atol=1e-6)
     assert torch.allclose(torch.from_numpy(gl).double(), cl, rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+@pytest.mark.parametrize("N,Lq,M,L,K,shared", [(3, 300, 8, 4, 4, False), (5, 777, 8, 4, 4, True), (2, 50, 4, 2, 4, False),
+                                                (1, 33, 8, 4, 8, False), (2, 19, 8, 1, 4, True)])
+def test_fused_frontend_vs_oracle(ops, N, Lq, M, L, K, shared, ref_dim):
+    """softmax + sampling-location arithmetic fused into the sampler == the module's ATen pre-ops + oracle core
+    (ops/modules/ms_deform_attn.py:98-108)."""
+    shapes = [(23, 31), (12, 16), (6, 8), (3, 4)][:L]
+    g = torch.Generator().manual_seed(N * 100 + Lq + ref_dim)
+    value, shapes_t, lsi, _, _ = O.make_inputs(N, 1, M, 32, shapes, K, 5)
+    value = torch.randn(value.shape, generator=g)
+    oa = torch.randn(N, Lq, M * L * K * 3, generator=g) * 2
+    ref = torch.rand((1 if shared else N), Lq, L, ref_dim, generator=g)
+    if ref_dim == 4:
+        ref[..., 2:] *= 0.3
+    n_off = M * L * K * 2
+    off = oa[..., :n_off].reshape(N, Lq, M, L, K, 2)
+    attn = torch.softmax(oa[..., n_off:].reshape(N, Lq, M, L * K), -1).view(N, Lq, M, L, K)
+    r = ref.expand(N, -1, -1, -1)
+    if ref_dim == 2:
+        norm = torch.stack([shapes_t[:, 1], shapes_t[:, 0]], -1).float()
+        loc = r[:, :, None, :, None, :] + off / norm[None, None, None, :, None, :]
+    else:
+        loc = r[:, :, None, :, None, :2] + off / K * r[:, :, None, :, None, 2:] * 0.5
+    want = O.forward_c(value, shapes_t, lsi, loc, attn, np.float32)
+    got = ops.ms_deform_attn_fused(value.cuda(), shapes_t.cuda(), lsi.cuda(), oa.cuda(), ref.cuda(), L, K)
+    assert _variant() == "fwd_fused_f32_d32_tma"
+    assert torch.allclose(got.cpu(), want, rtol=1e-4, atol=2e-5)
+    # strided projection rows (the op reads them in place out of a wider GEMM output)
+    wide = torch.zeros(N, Lq, oa.shape[-1] + 64)
+    wide[..., :oa.shape[-1]] = oa
+    got2 = ops.ms_deform_attn_fused(value.cuda(), shapes_t.cuda(), lsi.cuda(), wide.cuda()[..., :oa.shape[-1]],
+                                    ref.cuda(), L, K)
+    assert torch.equal(got2, got)

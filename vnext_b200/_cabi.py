@@ -18,6 +18,8 @@ SIGNATURES = {
     "vnext_launch_count": (ctypes.c_ulonglong, []),
     "vnext_msda_last_variant": (ctypes.c_char_p, []),
     "vnext_msda_forward": (_c_int, [_c_int] + [_c_void_p] * 5 + [_c_int] * 7 + [_c_void_p, _c_void_p]),
+    "vnext_msda_forward_fused": (_c_int, [_c_int] + [_c_void_p] * 4 + [_c_int, _c_void_p, _c_int, _c_int] + [_c_int] * 7
+                                 + [_c_void_p, _c_void_p]),
     "vnext_msda_backward": (_c_int, [_c_int] + [_c_void_p] * 6 + [_c_int] * 7 + [_c_void_p] * 5),
     "vnext_msda_backward_workspace_bytes": (_c_size_t, [_c_int] * 5),
     "vnext_linear_tf32": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_int,

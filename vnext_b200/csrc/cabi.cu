@@ -39,6 +39,10 @@ int msda_backward_device(int dtype, const void *value, const int64_t *shapes, co
                          const void *attn, const void *gout, int N, int S, int M, int D, int L, int Lq, int K,
                          void *gvalue, void *gloc, void *gattn, void *workspace, cudaStream_t stream);
 
+int msda_forward_fused_device(int dtype, const void *value, const int64_t *shapes, const int64_t *lsi, const float *oa,
+                              int oa_pitch, int n_off, const float *ref, int ref_dim, int ref_shared, int N, int S,
+                              int M, int D, int L, int Lq, int K, void *out, cudaStream_t stream);
+
 static int check_dims(const char *who, int dtype, int N, int S, int M, int D, int L, int Lq, int K) {
     VNEXT_CHECK_ARG(dtype == VNEXT_F32 || dtype == VNEXT_F64 || dtype == VNEXT_BF16, "%s: unsupported dtype %d", who,
                     dtype);
@@ -118,6 +122,23 @@ int vnext_msda_backward(int dtype, const void *value, const int64_t *spatial_sha
                                 grad_output, batch, spatial_size, num_heads, channels, num_levels, num_query,
                                 num_point, grad_value, grad_sampling_loc, grad_attn_weight, workspace,
                                 static_cast<cudaStream_t>(stream));
+}
+
+int vnext_msda_forward_fused(int dtype, const void *value, const int64_t *spatial_shapes,
+                             const int64_t *level_start_index, const float *offsets_logits, int row_pitch,
+                             const float *reference_points, int ref_dim, int ref_shared, int batch, int spatial_size,
+                             int num_heads, int channels, int num_levels, int num_query, int num_point, void *output,
+                             void *stream) {
+    int rc = check_dims("vnext_msda_forward_fused", dtype, batch, spatial_size, num_heads, channels, num_levels,
+                        num_query, num_point);
+    if (rc) return rc;
+    const bool empty = (long long)batch * num_query == 0;
+    VNEXT_CHECK_ARG(empty || (value && spatial_shapes && level_start_index && offsets_logits && reference_points && output),
+                    "vnext_msda_forward_fused: null tensor pointer");
+    return msda_forward_fused_device(dtype, value, spatial_shapes, level_start_index, offsets_logits, row_pitch,
+                                     num_heads * num_levels * num_point * 2, reference_points, ref_dim, ref_shared, batch,
+                                     spatial_size, num_heads, channels, num_levels, num_query, num_point, output,
+                                     static_cast<cudaStream_t>(stream));
 }
 
 size_t vnext_msda_backward_workspace_bytes(int dtype, int batch, int spatial_size, int num_heads, int channels) {

@@ -82,6 +82,36 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     return out
 
 
+def ms_deform_attn_fused(value, spatial_shapes, level_start_index, offsets_logits, reference_points, n_levels, n_points):
+    """Fused module core: softmax + sampling locations + sampling (include/vnext_b200.h: vnext_msda_forward_fused).
+    value [N,S,M,32]; offsets_logits [N,Lq,M*L*P*3] (rows may be strided); reference_points [N|1, Lq, L, 2|4]."""
+    if not value.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")
+    N, S, M, D = value.shape
+    Lq = offsets_logits.shape[1]
+    L, P = n_levels, n_points
+    _require(value.is_contiguous() and offsets_logits.stride(-1) == 1 and reference_points.is_contiguous(),
+             "value / reference_points must be contiguous and offsets_logits row-contiguous")
+    _require(offsets_logits.dtype == torch.float32 and reference_points.dtype == torch.float32,
+             "offsets_logits and reference_points must be float32")
+    ol = offsets_logits.reshape(N * Lq, offsets_logits.shape[-1])
+    ref_shared = int(reference_points.shape[0] == 1 and N > 1) if reference_points.dim() == 4 else 0
+    _require(reference_points.shape[-3:-1] == (Lq, L) and reference_points.shape[0] in (1, N),
+             "reference_points must be [N|1, Lq, L, 2|4]")
+    out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+    e = value.element_size()
+    info = {"bytes": float(N) * (e * S * M * D + 4 * 3 * Lq * M * L * P + e * Lq * M * D), "N": N, "Lq": Lq, "S": S}
+    with torch.cuda.device(value.device):
+        rc = _cabi.timed_call(
+            "msda_fused_enc" if Lq == S else "msda_fused_dec", info, value,
+            lambda: _cabi.lib().vnext_msda_forward_fused(
+                _DTYPES[value.dtype], value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                ol.data_ptr(), ol.stride(0), reference_points.data_ptr(), reference_points.shape[-1],
+                1 if reference_points.shape[0] == 1 else 0, N, S, M, D, L, Lq, P, out.data_ptr(), _stream(value)))
+    _cabi.check(rc, "ms_deform_attn_fused")
+    return out
+
+
 def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
                             im2col_step):
     N, S, M, D, L, Lq, P = _check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,

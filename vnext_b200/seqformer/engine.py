@@ -217,6 +217,11 @@ class SeqFormerEngine:
         """value [N,S,M,D]; oa [N,Lq,n_off + M*L*P] raw offsets|logits; ref [N|1, Lq, L, 2|4] -> [N, Lq, C]."""
         N, Lq = oa.shape[0], oa.shape[1]
         M, L, P = self.M, self.L, self.P
+        if self.native:      # softmax + location arithmetic + sampling in one kernel
+            from .. import msda
+            if oa.stride(0) == 0:                       # decoder layer 0: one projection shared by all frames
+                oa = oa.contiguous()
+            return msda.ms_deform_attn_fused(value.contiguous(), plan.shapes, plan.lsi, oa, ref.contiguous(), L, P)
         off = oa[..., :n_off].reshape(N, Lq, M, L, P, 2)
         attn = torch.softmax(oa[..., n_off:].reshape(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
         if ref.shape[-1] == 2:
