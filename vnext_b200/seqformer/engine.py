@@ -90,6 +90,10 @@ class SeqFormerEngine:
         # the plain-torch formulation below each `if self.native` is the same math and is what the CPU unit
         # tests of the host logic exercise (with an injected sampler).
         self.native = (self.device.type == "cuda") and msda_impl is None
+        # precision "tf32": projections / 1x1 convs on the hand-written tcgen05 TF32 GEMM (bench default; the
+        # precision PyTorch's conv path defaults to on the reference's GPU run).  precision "fp32": the same
+        # engine with the GEMMs on cuBLAS fp32 — the strict 1e-3 parity mode of the tests.
+        self.native_gemm = self.native and precision != "fp32"
         self._plans: Dict[Tuple[int, int, int], ClipPlan] = {}
         sd = state_dict
         dev = self.device
@@ -194,7 +198,7 @@ class SeqFormerEngine:
         plan.extra["lsi_list"] = starts                          # python ints: no device sync in the forward
         plan.extra["scale_wh"] = torch.tensor([float(W), float(H)], device=dev)
         plan.extra["mask_u8"] = plan.mask_flat[0].to(torch.uint8).contiguous()
-        if self.native:
+        if self.native_gemm:
             # (x + pos) W_oa + b  ==  x W_oa + (pos W_oa + b): the clip geometry's share of the offset/attention
             # projection, once per layer per plan (exact fp32), consumed as a row-periodic bias by the GEMM epilogue
             prev = torch.backends.cuda.matmul.allow_tf32
@@ -202,6 +206,7 @@ class SeqFormerEngine:
             plan.extra["enc_posproj"] = [F.linear(plan.pos_flat[0], w["attn"]["oa_w"], w["attn"]["oa_b"]).contiguous()
                                          for w in self.enc]
             torch.backends.cuda.matmul.allow_tf32 = prev
+        if self.native:
             plan.extra["gn_ws"] = torch.empty(2 * T * 32, dtype=torch.float32, device=dev)
         self._plans[key] = plan
         return plan
@@ -247,7 +252,7 @@ class SeqFormerEngine:
 
     def lin(self, x, wb, relu=False, residual=None, ln=None, **kw):
         """y = [relu]( [LayerNorm]( x W^T + b [+ residual] ) ) — one tcgen05 kernel when native."""
-        if self.native:
+        if self.native_gemm:
             from ..linear import linear
             if residual is not None and residual.shape != x.shape[:-1] + (wb[0].shape[0],):
                 residual = residual.expand(*x.shape[:-1], wb[0].shape[0])
@@ -362,7 +367,7 @@ class SeqFormerEngine:
         return torch.cat(toks, 1)                      # [T, S, C]
 
     def _value(self, x, attn_w, plan):
-        if self.native:      # padding rows zeroed in the GEMM epilogue
+        if self.native_gemm:      # padding rows zeroed in the GEMM epilogue
             kw = {"row_mask": plan.extra["mask_u8"], "mask_cols": self.C} if plan.any_pad else {}
             v = self.lin(x, (attn_w["v_w"], attn_w["v_b"]), **kw)
         else:
@@ -374,7 +379,7 @@ class SeqFormerEngine:
     def encoder(self, x, plan):
         for i, w in enumerate(self.enc):
             a = w["attn"]
-            if self.native:
+            if self.native_gemm:
                 oa = self.lin(x, (a["oa_w"], None), bias2d=plan.extra["enc_posproj"][i])
             else:
                 oa = F.linear(x + plan.pos_flat, a["oa_w"], a["oa_b"])
