@@ -32,6 +32,16 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *t
         "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// shared -> global tile store (TMA); rows / columns beyond the tensor extent are clipped by the hardware
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tmap, const void *smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
@@ -120,6 +130,7 @@ struct GemmParams {
     int ldo, ldr;
     int flags;
     int vec_ok;              // out / residual / bias rows allow 16-byte vector access
+    int tma_epi;             // epilogue tiles go through shared memory + TMA (coalesced); else direct row stores
     float eps;
     int num_m_tiles, num_n_tiles;
 };
@@ -128,10 +139,22 @@ constexpr int kGemmThreads = 256;
 constexpr int BLOCK_M = 128;
 
 // x[j] = acc + bias + bias2d + residual for 32 consecutive columns starting at global column `col0` of `row`
-__device__ __forceinline__ void epilogue_add(const GemmParams &p, int row, bool row_ok, int col0, uint32_t (&v)[32]) {
+// smem_res: this thread's residual row segment in a SWIZZLE_128B staging tile (or null -> read global memory)
+__device__ __forceinline__ void epilogue_add(const GemmParams &p, int row, bool row_ok, int col0, uint32_t (&v)[32],
+                                             const unsigned char *smem_res = nullptr, int swz = 0) {
     const bool vec = p.vec_ok && (col0 + 32 <= p.N);
     const float *b2 = p.bias2d ? p.bias2d + (size_t)(row % p.period) * p.ldb2 + col0 : nullptr;
-    const float *rr = (p.flags & EPI_RESIDUAL) ? p.residual + (size_t)row * p.ldr + col0 : nullptr;
+    const float *rr = ((p.flags & EPI_RESIDUAL) && !smem_res) ? p.residual + (size_t)row * p.ldr + col0 : nullptr;
+    if (smem_res) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 r = *reinterpret_cast<const float4 *>(smem_res + ((j ^ swz) << 4));
+            v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + r.x);
+            v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + r.y);
+            v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + r.z);
+            v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + r.w);
+        }
+    }
     if (vec) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -168,7 +191,9 @@ __device__ __forceinline__ void epilogue_add(const GemmParams &p, int row, bool 
 
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
+                 const GemmParams p) {
     constexpr int BLOCK_K = 32;                 // fp32 elements = 128 bytes = one swizzle row
     constexpr int UMMA_K = 8;                   // 32 bytes of tf32
     constexpr int A_BYTES = BLOCK_M * 128, B_BYTES = BLOCK_N * 128;
@@ -180,7 +205,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[ACC_STAGES], tmem_empty[ACC_STAGES];
+    __shared__ __align__(8) uint64_t res_bar[4][2];            // per epilogue warp, per residual buffer
     __shared__ uint32_t tmem_base_smem;
+    // epilogue staging after the operand ring: per warp 2 output + 2 residual tiles of 32 rows x 128 B (swizzled)
+    unsigned char *const epi_smem = smem + STAGES * STAGE_BYTES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
@@ -200,6 +228,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int s = 0; s < ACC_STAGES; ++s) {
             mbar_init(&tmem_full[s], 1);
             mbar_init(&tmem_empty[s], 4);
+        }
+        for (int w = 0; w < 4; ++w) {
+            mbar_init(&res_bar[w][0], 1);
+            mbar_init(&res_bar[w][1], 1);
         }
         fence_mbar_init();
     }
@@ -253,86 +285,129 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int ew = warp - 4;                                   // TMEM lane quarter this warp may touch
         int acc = 0, acc_phase = 0;
         const bool relu = (p.flags & EPI_RELU) != 0;
+        const bool has_res = (p.flags & EPI_RESIDUAL) != 0;
+        const bool tma_epi = p.tma_epi != 0;
+        unsigned char *const out_buf = epi_smem + ew * 16384;       // 2 x 4 KB
+        unsigned char *const res_buf = out_buf + 8192;              // 2 x 4 KB
+        const int swz = lane & 7;                                   // SWIZZLE_128B: 16-B chunk j of row r lives at j ^ (r & 7)
+        uint32_t chunk_count = 0;                                   // output staging buffers used so far (parity of buffer)
+        uint32_t res_issued = 0, res_waited = 0;                    // residual tiles requested / consumed
+        if (tma_epi && lane == 0) {
+            prefetch_tmap(&tmap_out);
+            if (has_res) prefetch_tmap(&tmap_res);
+        }
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_idx = (tile / p.num_n_tiles) * BLOCK_M, n_idx = (tile % p.num_n_tiles) * BLOCK_N;
+            const int row0 = m_idx + ew * 32;
+            const int row = row0 + lane;
+            const bool row_ok = row < p.M;
+            const int n_chunks = min(BLOCK_N, p.N - n_idx + 31) / 32;   // 32-column chunks that hold real columns
+            // residual tile of chunk 0 can be in flight while we wait for the accumulator
+            if (tma_epi && has_res && lane == 0) {
+                mbar_expect_tx(&res_bar[ew][res_issued & 1], 4096);
+                tma_load_2d(res_buf + (res_issued & 1) * 4096, &tmap_res, n_idx, row0, &res_bar[ew][res_issued & 1]);
+            }
+            if (tma_epi && has_res) ++res_issued;
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
-            const int row = m_idx + ew * 32 + lane;
-            const bool row_ok = row < p.M;
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
             float *orow = p.out + (size_t)row * p.ldo;
             const bool masked = p.row_mask && row_ok && p.row_mask[row % p.period] != 0;
-            if (p.flags & EPI_LAYERNORM) {
-                // pass 1: x = acc + bias (+ residual), parked back in TMEM; thread-local mean / variance (lane == row)
+            const bool ln = (p.flags & EPI_LAYERNORM) != 0;
+            float mean = 0.f, rstd = 1.f;
+            // LayerNorm: pass 0 parks x = acc + bias (+ residual) in TMEM and gathers thread-local statistics
+            // (TMEM lane == output row); pass 1 normalises and stores.  Without LayerNorm there is only pass 1.
+            for (int pass = ln ? 0 : 1; pass < 2; ++pass) {
                 float sum = 0.f, sumsq = 0.f;
 #pragma unroll 1
-                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                for (int c = 0; c < n_chunks; ++c) {
+                    const int c0 = c * 32, col0 = n_idx + c0;
                     uint32_t v[32];
                     tmem_ld32(taddr + c0, v);
                     tmem_ld_wait();
-                    epilogue_add(p, row, row_ok, n_idx + c0, v);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float x = __uint_as_float(v[j]);
-                        sum += x;
-                        sumsq = fmaf(x, x, sumsq);
+                    if (pass == 0 || !ln) {
+                        const unsigned char *rrow = nullptr;
+                        if (tma_epi && has_res) {
+                            if (lane == 0 && c + 1 < n_chunks) {        // prefetch the next residual tile
+                                mbar_expect_tx(&res_bar[ew][res_issued & 1], 4096);
+                                tma_load_2d(res_buf + (res_issued & 1) * 4096, &tmap_res, col0 + 32, row0,
+                                            &res_bar[ew][res_issued & 1]);
+                            }
+                            if (c + 1 < n_chunks) ++res_issued;
+                            mbar_wait(&res_bar[ew][res_waited & 1], (res_waited >> 1) & 1);
+                            rrow = res_buf + (res_waited & 1) * 4096 + lane * 128;
+                            ++res_waited;
+                        }
+                        epilogue_add(p, row, row_ok, col0, v, rrow, swz);
+                        if (rrow) __syncwarp();                          // all lanes done with the tile before it is refilled
                     }
-                    tmem_st32(taddr + c0, v);
-                }
-                tmem_st_wait();
-                const float mean = sum * (1.f / BLOCK_N);
-                const float var = fmaxf(sumsq * (1.f / BLOCK_N) - mean * mean, 0.f);
-                const float rstd = rsqrtf(var + p.eps);
-#pragma unroll 1
-                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + c0, v);
-                    tmem_ld_wait();
-                    if (row_ok) {
+                    if (pass == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float x = __uint_as_float(v[j]);
+                            sum += x;
+                            sumsq = fmaf(x, x, sumsq);
+                        }
+                        tmem_st32(taddr + c0, v);
+                        continue;
+                    }
+                    if (ln) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            const float4 g = *reinterpret_cast<const float4 *>(p.gamma + n_idx + c0 + j);
-                            const float4 be = *reinterpret_cast<const float4 *>(p.beta + n_idx + c0 + j);
-                            float4 o;
-                            o.x = (__uint_as_float(v[j]) - mean) * rstd * g.x + be.x;
-                            o.y = (__uint_as_float(v[j + 1]) - mean) * rstd * g.y + be.y;
-                            o.z = (__uint_as_float(v[j + 2]) - mean) * rstd * g.z + be.z;
-                            o.w = (__uint_as_float(v[j + 3]) - mean) * rstd * g.w + be.w;
-                            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                            *reinterpret_cast<float4 *>(orow + n_idx + c0 + j) = o;
+                            const float4 g = *reinterpret_cast<const float4 *>(p.gamma + col0 + j);
+                            const float4 be = *reinterpret_cast<const float4 *>(p.beta + col0 + j);
+                            v[j] = __float_as_uint((__uint_as_float(v[j]) - mean) * rstd * g.x + be.x);
+                            v[j + 1] = __float_as_uint((__uint_as_float(v[j + 1]) - mean) * rstd * g.y + be.y);
+                            v[j + 2] = __float_as_uint((__uint_as_float(v[j + 2]) - mean) * rstd * g.z + be.z);
+                            v[j + 3] = __float_as_uint((__uint_as_float(v[j + 3]) - mean) * rstd * g.w + be.w);
                         }
                     }
-                }
-            } else {
-#pragma unroll 1
-                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-                    if (n_idx + c0 >= p.N) break;                  // warp-uniform
-                    uint32_t v[32];
-                    tmem_ld32(taddr + c0, v);
-                    tmem_ld_wait();
-                    epilogue_add(p, row, row_ok, n_idx + c0, v);
-                    if (row_ok) {
-                        const int col0 = n_idx + c0;
+                    if (relu) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaxf(__uint_as_float(v[j]), 0.f));
+                    }
+                    if (masked) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < p.mask_cols) v[j] = 0u;
+                    }
+                    if (tma_epi) {
+                        unsigned char *ob = out_buf + (chunk_count & 1) * 4096;
+                        if (chunk_count >= 2) {                          // the TMA store that last read this buffer is done
+                            if (lane == 0) tma_store_wait_read<1>();
+                            __syncwarp();
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4 *>(ob + lane * 128 + ((j ^ swz) << 4)) =
+                                make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                            __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmap_out, ob, col0, row0);
+                            tma_store_commit();
+                        }
+                        ++chunk_count;
+                    } else if (row_ok) {
                         if (p.vec_ok && col0 + 32 <= p.N) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                       __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                                if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                                if (masked && col0 + j < p.mask_cols) o = make_float4(0.f, 0.f, 0.f, 0.f);
-                                *reinterpret_cast<float4 *>(orow + col0 + j) = o;
-                            }
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4 *>(orow + col0 + j) =
+                                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
                         } else {
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
-                                if (col0 + j < p.N) {
-                                    float o = __uint_as_float(v[j]);
-                                    if (relu) o = fmaxf(o, 0.f);
-                                    if (masked && col0 + j < p.mask_cols) o = 0.f;
-                                    orow[col0 + j] = o;
-                                }
+                                if (col0 + j < p.N) orow[col0 + j] = __uint_as_float(v[j]);
                         }
                     }
+                }
+                if (pass == 0) {
+                    tmem_st_wait();
+                    mean = sum * (1.f / BLOCK_N);
+                    const float var = fmaxf(sumsq * (1.f / BLOCK_N) - mean * mean, 0.f);
+                    rstd = rsqrtf(var + p.eps);
                 }
             }
             tcgen05_fence_before();
@@ -340,6 +415,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
+        if (tma_epi && lane == 0) tma_store_wait_all();             // stores must land before the CTA exits
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -389,9 +465,10 @@ static int make_tmap_f32(CUtensorMap *tm, const float *ptr, int rows, int cols, 
 }
 
 template <int BLOCK_N, int STAGES>
-static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, GemmParams p, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &to, const CUtensorMap &tr,
+                       GemmParams p, cudaStream_t stream) {
     auto kern = gemm_tf32_kernel<BLOCK_N, STAGES>;
-    constexpr size_t smem = (size_t)STAGES * (BLOCK_M * 128 + BLOCK_N * 128) + 1024;
+    constexpr size_t smem = (size_t)STAGES * (BLOCK_M * 128 + BLOCK_N * 128) + 4 * 16384 + 1024;
     static bool configured = false;
     if (!configured) {
         VNEXT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -401,7 +478,7 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, GemmParams 
     p.num_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, kGemmThreads, smem, stream>>>(ta, tb, p);
+    kern<<<grid, kGemmThreads, smem, stream>>>(ta, tb, to, tr, p);
     count_launch();
     VNEXT_CUDA(cudaGetLastError());
     return VNEXT_OK;
@@ -437,12 +514,24 @@ int linear_tf32_device(const LinearArgs &x, cudaStream_t stream) {
             return VNEXT_EINVAL;
         }
     }
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, to, tr;
     int rc = make_tmap_f32(&ta, x.a, x.M, x.K, x.lda, BLOCK_M);
     if (rc) return rc;
     rc = make_tmap_f32(&tb, x.w, x.N, x.K, x.K, wide ? 256 : 128);
     if (rc) return rc;
-    return wide ? launch_gemm<256, 4>(ta, tb, p, stream) : launch_gemm<128, 6>(ta, tb, p, stream);
+    // coalesced epilogue through shared memory + TMA needs 16-byte aligned rows of out (and residual)
+    p.tma_epi = al16(x.out) && x.ldo % 4 == 0 && (!x.residual || (al16(x.residual) && x.ldr % 4 == 0));
+    to = ta;
+    tr = ta;
+    if (p.tma_epi) {
+        rc = make_tmap_f32(&to, x.out, x.M, x.N, x.ldo, 32);
+        if (rc) return rc;
+        if (x.residual) {
+            rc = make_tmap_f32(&tr, x.residual, x.M, x.N, x.ldr, 32);
+            if (rc) return rc;
+        }
+    }
+    return wide ? launch_gemm<256, 3>(ta, tb, to, tr, p, stream) : launch_gemm<128, 4>(ta, tb, to, tr, p, stream);
 }
 
 }  // namespace vnext
