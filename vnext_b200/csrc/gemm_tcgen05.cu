@@ -135,57 +135,33 @@ struct GemmParams {
     int num_m_tiles, num_n_tiles;
 };
 
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;      // warps 0-3: TMA / MMA / TMEM-alloc / idle; warps 4-11: epilogue
+constexpr int kEpiWarps = 8;           // two warps per TMEM lane quarter, interleaving the 32-column chunks
 constexpr int BLOCK_M = 128;
 
 // x[j] = acc + bias + bias2d + residual for 32 consecutive columns starting at global column `col0` of `row`
-// smem_res: this thread's residual row segment in a SWIZZLE_128B staging tile (or null -> read global memory)
-__device__ __forceinline__ void epilogue_add(const GemmParams &p, int row, bool row_ok, int col0, uint32_t (&v)[32],
-                                             const unsigned char *smem_res = nullptr, int swz = 0) {
-    const bool vec = p.vec_ok && (col0 + 32 <= p.N);
+// the parts of the epilogue sum that still come from global memory: row-periodic 2-D bias, and the residual when
+// the TMA path is unavailable (unaligned rows)
+__device__ __forceinline__ void epilogue_add_global(const GemmParams &p, int row, bool row_ok, int col0, uint32_t (&v)[32]) {
+    if (!row_ok) return;
     const float *b2 = p.bias2d ? p.bias2d + (size_t)(row % p.period) * p.ldb2 + col0 : nullptr;
-    const float *rr = ((p.flags & EPI_RESIDUAL) && !smem_res) ? p.residual + (size_t)row * p.ldr + col0 : nullptr;
-    if (smem_res) {
+    const float *rr = ((p.flags & EPI_RESIDUAL) && !p.tma_epi) ? p.residual + (size_t)row * p.ldr + col0 : nullptr;
+    const bool vec = p.vec_ok && (col0 + 32 <= p.N);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float4 r = *reinterpret_cast<const float4 *>(smem_res + ((j ^ swz) << 4));
-            v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + r.x);
-            v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + r.y);
-            v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + r.z);
-            v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + r.w);
-        }
-    }
-    if (vec) {
+    for (int j = 0; j < 32; j += 4) {
+        float x[4] = {__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])};
+        if (vec) {
+            if (b2) { const float4 b = *reinterpret_cast<const float4 *>(b2 + j); x[0] += b.x; x[1] += b.y; x[2] += b.z; x[3] += b.w; }
+            if (rr) { const float4 r = *reinterpret_cast<const float4 *>(rr + j); x[0] += r.x; x[1] += r.y; x[2] += r.z; x[3] += r.w; }
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            float4 x = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                   __uint_as_float(v[j + 3]));
-            if (p.bias) {
-                const float4 b = *reinterpret_cast<const float4 *>(p.bias + col0 + j);
-                x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
-            }
-            if (b2 && row_ok) {
-                const float4 b = *reinterpret_cast<const float4 *>(b2 + j);
-                x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
-            }
-            if (rr && row_ok) {
-                const float4 r = *reinterpret_cast<const float4 *>(rr + j);
-                x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
-            }
-            v[j] = __float_as_uint(x.x); v[j + 1] = __float_as_uint(x.y);
-            v[j + 2] = __float_as_uint(x.z); v[j + 3] = __float_as_uint(x.w);
+            for (int t = 0; t < 4; ++t)
+                if (col0 + j + t < p.N) {
+                    if (b2) x[t] += b2[j + t];
+                    if (rr) x[t] += rr[j + t];
+                }
         }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(v[j]);
-            if (col0 + j < p.N) {
-                if (p.bias) x += p.bias[col0 + j];
-                if (b2 && row_ok) x += b2[j];
-                if (rr && row_ok) x += rr[j];
-            }
-            v[j] = __float_as_uint(x);
-        }
+        v[j] = __float_as_uint(x[0]); v[j + 1] = __float_as_uint(x[1]); v[j + 2] = __float_as_uint(x[2]); v[j + 3] = __float_as_uint(x[3]);
     }
 }
 
@@ -205,7 +181,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[ACC_STAGES], tmem_empty[ACC_STAGES];
-    __shared__ __align__(8) uint64_t res_bar[4][2];            // per epilogue warp, per residual buffer
+    __shared__ __align__(8) uint64_t res_bar[kEpiWarps];       // per epilogue warp: its residual staging tile
+    __shared__ __align__(16) float s_bias[3][256];             // bias / gamma / beta of the current n-tile
+    __shared__ float2 s_lnstat[kEpiWarps][32];                 // LayerNorm partial (sum, sumsq) exchange between warp halves
     __shared__ uint32_t tmem_base_smem;
     // epilogue staging after the operand ring: per warp 2 output + 2 residual tiles of 32 rows x 128 B (swizzled)
     unsigned char *const epi_smem = smem + STAGES * STAGE_BYTES;
@@ -227,12 +205,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
         for (int s = 0; s < ACC_STAGES; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], 4);
+            mbar_init(&tmem_empty[s], kEpiWarps);
         }
-        for (int w = 0; w < 4; ++w) {
-            mbar_init(&res_bar[w][0], 1);
-            mbar_init(&res_bar[w][1], 1);
-        }
+        for (int w = 0; w < kEpiWarps; ++w) mbar_init(&res_bar[w], 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -250,7 +225,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         int stage = 0, phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_idx = (tile / p.num_n_tiles) * BLOCK_M, n_idx = (tile % p.num_n_tiles) * BLOCK_N;
-            for (int kb = 0; kb < num_k_blocks; ++kb) {
+            // every CTA walks K from a different starting block: all SMs want the same weight tile at about the
+            // same time, and starting them at different k spreads those requests over the L2 slices
+            const int k_rot = (int)(blockIdx.x % (unsigned)num_k_blocks);
+            for (int kb0 = 0; kb0 < num_k_blocks; ++kb0) {
+                int kb = kb0 + k_rot;
+                if (kb >= num_k_blocks) kb -= num_k_blocks;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 unsigned char *sa = smem + stage * STAGE_BYTES, *sb = sa + A_BYTES;
                 mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
@@ -281,17 +261,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue =====================
-        const int ew = warp - 4;                                   // TMEM lane quarter this warp may touch
+        // ===================== epilogue (8 warps) =====================
+        const int ewi = warp - 4;                                   // 0..7
+        const int ew = ewi & 3;                                     // TMEM lane quarter this warp may touch (warp % 4)
+        const int half = ewi >> 2;                                  // which interleaved half of the column chunks
         int acc = 0, acc_phase = 0;
         const bool relu = (p.flags & EPI_RELU) != 0;
         const bool has_res = (p.flags & EPI_RESIDUAL) != 0;
         const bool tma_epi = p.tma_epi != 0;
-        unsigned char *const out_buf = epi_smem + ew * 16384;       // 2 x 4 KB
-        unsigned char *const res_buf = out_buf + 8192;              // 2 x 4 KB
-        const int swz = lane & 7;                                   // SWIZZLE_128B: 16-B chunk j of row r lives at j ^ (r & 7)
-        uint32_t chunk_count = 0;                                   // output staging buffers used so far (parity of buffer)
-        uint32_t res_issued = 0, res_waited = 0;                    // residual tiles requested / consumed
+        const bool ln = (p.flags & EPI_LAYERNORM) != 0;
+        // staging: two 4-KB tiles (32 rows x 128 B, SWIZZLE_128B) per warp.  With a residual: [0] = out, [1] = residual;
+        // without: both are output buffers (double-buffered TMA stores).
+        unsigned char *const buf0 = epi_smem + ewi * 8192;
+        unsigned char *const buf1 = buf0 + 4096;
+        const int swz = lane & 7;                                   // 16-B chunk j of row r lives at j ^ (r & 7)
+        uint32_t stores = 0, res_loads = 0;
+        int bias_n_idx = -1;
         if (tma_epi && lane == 0) {
             prefetch_tmap(&tmap_out);
             if (has_res) prefetch_tmap(&tmap_res);
@@ -302,44 +287,69 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int row = row0 + lane;
             const bool row_ok = row < p.M;
             const int n_chunks = min(BLOCK_N, p.N - n_idx + 31) / 32;   // 32-column chunks that hold real columns
-            // residual tile of chunk 0 can be in flight while we wait for the accumulator
-            if (tma_epi && has_res && lane == 0) {
-                mbar_expect_tx(&res_bar[ew][res_issued & 1], 4096);
-                tma_load_2d(res_buf + (res_issued & 1) * 4096, &tmap_res, n_idx, row0, &res_bar[ew][res_issued & 1]);
+            if (n_idx != bias_n_idx) {                                  // (re)load the per-column vectors of this n-tile
+                asm volatile("bar.sync 1, 256;" ::: "memory");          // everyone is done with the previous vectors
+                const int t = threadIdx.x - 128;                        // 0..255
+                const int col = n_idx + t;
+                if (t < BLOCK_N) {
+                    s_bias[0][t] = (p.bias && col < p.N) ? p.bias[col] : 0.f;
+                    if (ln) {
+                        s_bias[1][t] = col < p.N ? p.gamma[col] : 0.f;
+                        s_bias[2][t] = col < p.N ? p.beta[col] : 0.f;
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                bias_n_idx = n_idx;
             }
-            if (tma_epi && has_res) ++res_issued;
+            if (tma_epi && has_res && half < n_chunks) {                // first residual tile: in flight while we wait
+                if (lane == 0) {
+                    mbar_expect_tx(&res_bar[ewi], 4096);
+                    tma_load_2d(buf1, &tmap_res, n_idx + half * 32, row0, &res_bar[ewi]);
+                }
+            }
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
             float *orow = p.out + (size_t)row * p.ldo;
             const bool masked = p.row_mask && row_ok && p.row_mask[row % p.period] != 0;
-            const bool ln = (p.flags & EPI_LAYERNORM) != 0;
             float mean = 0.f, rstd = 1.f;
             // LayerNorm: pass 0 parks x = acc + bias (+ residual) in TMEM and gathers thread-local statistics
-            // (TMEM lane == output row); pass 1 normalises and stores.  Without LayerNorm there is only pass 1.
+            // (TMEM lane == output row; the two warps of a lane quarter swap partial sums); pass 1 normalises and stores.
             for (int pass = ln ? 0 : 1; pass < 2; ++pass) {
                 float sum = 0.f, sumsq = 0.f;
 #pragma unroll 1
-                for (int c = 0; c < n_chunks; ++c) {
+                for (int c = half; c < n_chunks; c += 2) {
                     const int c0 = c * 32, col0 = n_idx + c0;
                     uint32_t v[32];
                     tmem_ld32(taddr + c0, v);
                     tmem_ld_wait();
-                    if (pass == 0 || !ln) {
+                    if ((pass == 0 || !ln) && !(p.flags & 0x200)) {
                         const unsigned char *rrow = nullptr;
                         if (tma_epi && has_res) {
-                            if (lane == 0 && c + 1 < n_chunks) {        // prefetch the next residual tile
-                                mbar_expect_tx(&res_bar[ew][res_issued & 1], 4096);
-                                tma_load_2d(res_buf + (res_issued & 1) * 4096, &tmap_res, col0 + 32, row0,
-                                            &res_bar[ew][res_issued & 1]);
-                            }
-                            if (c + 1 < n_chunks) ++res_issued;
-                            mbar_wait(&res_bar[ew][res_waited & 1], (res_waited >> 1) & 1);
-                            rrow = res_buf + (res_waited & 1) * 4096 + lane * 128;
-                            ++res_waited;
+                            mbar_wait(&res_bar[ewi], res_loads & 1);
+                            ++res_loads;
+                            rrow = buf1 + lane * 128;
                         }
-                        epilogue_add(p, row, row_ok, col0, v, rrow, swz);
-                        if (rrow) __syncwarp();                          // all lanes done with the tile before it is refilled
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {                    // bias from shared memory (broadcast reads)
+                            const float4 b = *reinterpret_cast<const float4 *>(&s_bias[0][c0 + 4 * j]);
+                            float4 x = make_float4(__uint_as_float(v[4 * j]) + b.x, __uint_as_float(v[4 * j + 1]) + b.y,
+                                                   __uint_as_float(v[4 * j + 2]) + b.z, __uint_as_float(v[4 * j + 3]) + b.w);
+                            if (rrow) {
+                                const float4 r = *reinterpret_cast<const float4 *>(rrow + ((j ^ swz) << 4));
+                                x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
+                            }
+                            v[4 * j] = __float_as_uint(x.x); v[4 * j + 1] = __float_as_uint(x.y);
+                            v[4 * j + 2] = __float_as_uint(x.z); v[4 * j + 3] = __float_as_uint(x.w);
+                        }
+                        if (rrow) {
+                            __syncwarp();                                // tile consumed by all lanes -> refill it
+                            if (lane == 0 && c + 2 < n_chunks) {
+                                mbar_expect_tx(&res_bar[ewi], 4096);
+                                tma_load_2d(buf1, &tmap_res, col0 + 64, row0, &res_bar[ewi]);
+                            }
+                        }
+                        if (p.bias2d || (has_res && !rrow)) epilogue_add_global(p, row, row_ok, col0, v);
                     }
                     if (pass == 0) {
 #pragma unroll
@@ -354,8 +364,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (ln) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            const float4 g = *reinterpret_cast<const float4 *>(p.gamma + col0 + j);
-                            const float4 be = *reinterpret_cast<const float4 *>(p.beta + col0 + j);
+                            const float4 g = *reinterpret_cast<const float4 *>(&s_bias[1][c0 + j]);
+                            const float4 be = *reinterpret_cast<const float4 *>(&s_bias[2][c0 + j]);
                             v[j] = __float_as_uint((__uint_as_float(v[j]) - mean) * rstd * g.x + be.x);
                             v[j + 1] = __float_as_uint((__uint_as_float(v[j + 1]) - mean) * rstd * g.y + be.y);
                             v[j + 2] = __float_as_uint((__uint_as_float(v[j + 2]) - mean) * rstd * g.z + be.z);
@@ -371,10 +381,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         for (int j = 0; j < 32; ++j)
                             if (col0 + j < p.mask_cols) v[j] = 0u;
                     }
+                    if (p.flags & 0x100) continue;                       // debug: no output at all
                     if (tma_epi) {
-                        unsigned char *ob = out_buf + (chunk_count & 1) * 4096;
-                        if (chunk_count >= 2) {                          // the TMA store that last read this buffer is done
-                            if (lane == 0) tma_store_wait_read<1>();
+                        unsigned char *ob = (has_res || !(stores & 1)) ? buf0 : buf1;
+                        const int pending_ok = has_res ? 0 : 1;          // groups that may still be reading shared memory
+                        if (stores > (uint32_t)pending_ok) {
+                            if (lane == 0) {
+                                if (pending_ok) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+                            }
                             __syncwarp();
                         }
 #pragma unroll
@@ -388,7 +402,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             tma_store_2d(&tmap_out, ob, col0, row0);
                             tma_store_commit();
                         }
-                        ++chunk_count;
+                        ++stores;
                     } else if (row_ok) {
                         if (p.vec_ok && col0 + 32 <= p.N) {
 #pragma unroll
@@ -405,6 +419,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
                 if (pass == 0) {
                     tmem_st_wait();
+                    s_lnstat[ewi][lane] = make_float2(sum, sumsq);      // swap partials with the other half's warp
+                    asm volatile("bar.sync %0, 64;" ::"r"(2 + ew) : "memory");
+                    const float2 o = s_lnstat[ewi ^ 4][lane];
+                    sum += o.x;
+                    sumsq += o.y;
                     mean = sum * (1.f / BLOCK_N);
                     const float var = fmaxf(sumsq * (1.f / BLOCK_N) - mean * mean, 0.f);
                     rstd = rsqrtf(var + p.eps);
@@ -468,7 +487,7 @@ template <int BLOCK_N, int STAGES>
 static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &to, const CUtensorMap &tr,
                        GemmParams p, cudaStream_t stream) {
     auto kern = gemm_tf32_kernel<BLOCK_N, STAGES>;
-    constexpr size_t smem = (size_t)STAGES * (BLOCK_M * 128 + BLOCK_N * 128) + 4 * 16384 + 1024;
+    constexpr size_t smem = (size_t)STAGES * (BLOCK_M * 128 + BLOCK_N * 128) + kEpiWarps * 8192 + 1024;
     static bool configured = false;
     if (!configured) {
         VNEXT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -521,6 +540,7 @@ int linear_tf32_device(const LinearArgs &x, cudaStream_t stream) {
     if (rc) return rc;
     // coalesced epilogue through shared memory + TMA needs 16-byte aligned rows of out (and residual)
     p.tma_epi = al16(x.out) && x.ldo % 4 == 0 && (!x.residual || (al16(x.residual) && x.ldr % 4 == 0));
+    if (x.flags & 0x400) p.tma_epi = 0;                              // debug: force the direct-store epilogue
     to = ta;
     tr = ta;
     if (p.tma_epi) {
@@ -543,7 +563,7 @@ extern "C" int vnext_linear_tf32(const float *a, int lda, const float *weight, c
                                  const float *residual, int ldr, const float *ln_gamma, const float *ln_beta,
                                  float ln_eps, float *out, int ldo, int M, int N, int K, int flags, void *stream) {
     VNEXT_CHECK_ARG(M >= 0 && N >= 0 && K > 0, "vnext_linear_tf32: bad sizes M=%d N=%d K=%d", M, N, K);
-    VNEXT_CHECK_ARG(flags >= 0 && flags < 8, "vnext_linear_tf32: unknown epilogue flags %d", flags);
+    VNEXT_CHECK_ARG(flags >= 0 && flags < 0x800, "vnext_linear_tf32: unknown epilogue flags %d", flags);
     if (M == 0 || N == 0) return VNEXT_OK;
     VNEXT_CHECK_ARG(a && weight && out, "vnext_linear_tf32: null pointer");
     VNEXT_CHECK_ARG(al16(a) && al16(weight) && lda % 4 == 0 && K % 4 == 0,
