@@ -185,10 +185,8 @@ def own_arm(args, rank, world, local_rank):
     torch.cuda.synchronize()
     barrier()
     clocks = sampler.result()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    from vnext_b200.dist import max_over_ranks
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1), dev)
     fps = world * args.steps * T / (ms_total / 1e3)
 
     # ---- end to end through the reference-facing API: host frames in, host masks out, every step
@@ -201,10 +199,7 @@ def own_arm(args, rank, world, local_rank):
     for _ in range(args.steps):
         res = model(batched)
     torch.cuda.synchronize()
-    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_fps = world * args.steps * T / (float(e2e_ms.item()) / 1e3)
+    e2e_fps = world * args.steps * T / (max_over_ranks((time.perf_counter() - t0) * 1e3, dev) / 1e3)
 
     if rank != 0:
         return
@@ -219,20 +214,32 @@ def own_arm(args, rank, world, local_rank):
         for _ in range(3):
             eager.infer_video_device(frames_f, (H, W))
     agg = kt.summary()
-    roofline = None
-    kernels = {}
+    # group call sites into kernel families (one __global__ each) and rank by time inside a step
+    fam = {}
     for name, d in agg.items():
-        avg_us = d["us"] / d["calls"]
-        kernels[name] = {"calls_per_step": d["calls"] // 3, "avg_us": round(avg_us, 2),
-                         "GBps": round(d["bytes"] / d["calls"] / avg_us / 1e3, 1)}
-    if agg:
-        top = max(agg, key=lambda k: agg[k]["us"])
-        d = agg[top]
-        avg_us = d["us"] / d["calls"]
-        ach = d["bytes"] / d["calls"] / avg_us / 1e3
+        f = ("gemm_tf32_kernel" if name.startswith("linear_tf32") else
+             "msda_fwd_tile_kernel" if name.startswith("msda_") else name)
+        g = fam.setdefault(f, {"calls": 0, "us": 0.0, "bytes": 0.0, "flops": 0.0})
+        for k in g:
+            g[k] += d[k]
+    kernels = {f: {"calls_per_step": d["calls"] // 3, "us_per_step": round(d["us"] / 3, 1),
+                   "GBps": round(d["bytes"] / d["us"] / 1e3, 1),
+                   **({"TFLOPs": round(d["flops"] / d["us"] / 1e6, 1)} if d["flops"] else {})}
+               for f, d in sorted(fam.items(), key=lambda kv: -kv[1]["us"])}
+    roofline = None
+    if fam:
+        top = max(fam, key=lambda k: fam[k]["us"])
+        d = fam[top]
+        ach = d["bytes"] / d["us"] / 1e3
         roofline = {"kernel": top, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s",
                     "frac": round(ach / hbm, 4), "traffic": None, "peak_source": peak_src,
-                    "avg_us": round(avg_us, 2), "algorithmic_bytes_per_launch": d["bytes"] / d["calls"]}
+                    "launches_per_step": d["calls"] // 3, "avg_us": round(d["us"] / d["calls"], 2),
+                    "algorithmic_bytes_per_launch": round(d["bytes"] / d["calls"]),
+                    "note": "sum of algorithmic bytes over the family's launches in a step / their summed CUDA-event time"}
+        if "msda_fwd_tile_kernel" in fam:
+            m = fam["msda_fwd_tile_kernel"]
+            roofline["msda"] = {"achieved": round(m["bytes"] / m["us"] / 1e3, 1), "frac": round(m["bytes"] / m["us"] / 1e3 / hbm, 4),
+                                "us_per_step": round(m["us"] / 3, 1)}
 
     cpu = None
     if args.gpus == 1 and not args.no_cpu_baseline:
