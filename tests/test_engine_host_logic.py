@@ -54,3 +54,19 @@ def test_engine_matches_oracle_on_cpu(weights, name):
     assert torch.allclose(torch.tensor(got["pred_scores"]), torch.tensor(want["pred_scores"]), rtol=1e-3, atol=1e-4)
     agree = sum((a == b).float().mean().item() for a, b in zip(got["pred_masks"], want["pred_masks"]))
     assert agree / len(want["pred_masks"]) > 0.999
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_idol_engine_matches_oracle_on_cpu(name):
+    from oracle import idol_oracle as IO
+    from vnext_b200.idol.engine import IDOLEngine
+    from vnext_b200.idol.state_spec import idol_r50_state_spec
+    T, H, W, seed = CASES[name]
+    sd = fill_state_dict(idol_r50_state_spec(), seed)
+    frames = synthetic_clip(T, H, W, seed)
+    eng = IDOLEngine(sd, device="cpu", msda_impl=msda_oracle.forward_torch)
+    with torch.no_grad():
+        ref = IO.inference_forward(sd, frames)
+        out = eng.inference_forward(torch.stack(frames))
+    for k, tol in (("pred_logits", 1e-3), ("pred_boxes", 1e-4), ("pred_inst_embed", 1e-3), ("pred_masks", 5e-3)):
+        assert torch.allclose(out[k], ref[k], rtol=1e-3, atol=tol), k

@@ -158,8 +158,10 @@ class MSDeformAttnSeqFormer(_MSDeformAttnBase):
         out, loc, attn = self._core(qb.flatten(0, 1), reference_points.flatten(0, 1), value, input_spatial_shapes,
                                     input_level_start_index, want_locations=True)
         out = out.view(N, nf, Len_q, C)
-        # the reference returns the sampling locations / weights of the LAST frame of its loop
+        # the reference returns the sampling locations of the LAST frame of its loop, and the attention weights as it
+        # computed them: shared [N, Lq, M, L, P] in the first layer, per frame [N, nf, Lq, M, L, P] afterwards
         loc = loc.view(N, nf, *loc.shape[1:])[:, -1]
         attn = attn.view(N, nf, *attn.shape[1:])
-        attn = attn[:, -1] if query_box.dim() == 4 else attn[:, 0]
+        if query_box.dim() == 3:
+            attn = attn[:, 0]
         return self.output_proj(out), self.output_proj_box(out), loc, attn

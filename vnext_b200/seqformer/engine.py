@@ -129,6 +129,16 @@ class SeqFormerEngine:
             self.enc.append({"attn": packing.to_device(packing.pack_msda(sd, p + ".self_attn", box=False), dev),
                              "norm1": lin(p + ".norm1"), "lin1": lin(p + ".linear1"), "lin2": lin(p + ".linear2"),
                              "norm2": lin(p + ".norm2")})
+        self._pack_decoder(sd, lin, f32, dec_layers)
+        self.ref_point = lin(TR + "reference_points")
+        qe = f32(sd[DETR + "query_embed.weight"])
+        self.query_pos, self.tgt = qe[:, :self.C].unsqueeze(0).contiguous(), qe[:, self.C:].unsqueeze(0).contiguous()
+        self.controller = [lin(f"detr.controller.layers.{j}") for j in range(3)]
+        self.mask_head = {k: (cl(sd[f"detr.mask_head.{k}.weight"]), f32(sd[f"detr.mask_head.{k}.bias"]))
+                          for k in ("lay1", "lay2", "lay3", "lay4", "dcn")}
+
+    def _pack_decoder(self, sd, lin, f32, dec_layers):
+        dev = self.device
         self.dec = []
         for i in range(dec_layers):
             p = f"{TR}decoder.layers.{i}"
@@ -142,12 +152,6 @@ class SeqFormerEngine:
             d["bbox"] = [lin(f"{DETR}bbox_embed.{i}.layers.{j}") for j in range(3)]
             d["cls"] = lin(f"{DETR}class_embed.{i}")
             self.dec.append(d)
-        self.ref_point = lin(TR + "reference_points")
-        qe = f32(sd[DETR + "query_embed.weight"])
-        self.query_pos, self.tgt = qe[:, :self.C].unsqueeze(0).contiguous(), qe[:, self.C:].unsqueeze(0).contiguous()
-        self.controller = [lin(f"detr.controller.layers.{j}") for j in range(3)]
-        self.mask_head = {k: (cl(sd[f"detr.mask_head.{k}.weight"]), f32(sd[f"detr.mask_head.{k}.bias"]))
-                          for k in ("lay1", "lay2", "lay3", "lay4", "dcn")}
 
     # ------------------------------------------------------------------ geometry plan
     def plan(self, T, H, W) -> ClipPlan:
@@ -490,6 +494,8 @@ class SeqFormerEngine:
         feats [T, 8, H, W]; params [n, 169]; ref_px [T, n, 2]  ->  [n, T, 2H, 2W]
         (segmentation_condInst.py:404-493 without materialising the [1, n*10, H, W] tensor)."""
         T, cin, H, W = feats.shape
+        if params.dim() == 3:                       # IDOL: every frame has its own instance parameters
+            return self._dynamic_masks_per_frame(feats, params, ref_px, stride)
         n = params.shape[0]
         ch = 8
         w0 = params[:, :(cin + 2) * ch].reshape(n, ch, cin + 2)
@@ -509,6 +515,29 @@ class SeqFormerEngine:
         out = torch.einsum("nk,tnkp->tnp", w2, h2) + b2[None, :, None]
         out = self._aligned_bilinear(out.reshape(T * n, 1, H, W), stride // self.mask_stride)
         return out.view(T, n, out.shape[-2], out.shape[-1]).transpose(0, 1)
+
+    def _dynamic_masks_per_frame(self, feats, params, ref_px, stride=8):
+        """params [T, n, 169]; ref_px [T, n, 2] -> [T, n, 2H, 2W]."""
+        T, cin, H, W = feats.shape
+        n, ch = params.shape[1], 8
+        k0 = (cin + 2) * ch
+        w0 = params[..., :k0].reshape(T, n, ch, cin + 2)
+        w1 = params[..., k0:k0 + ch * ch].reshape(T, n, ch, ch)
+        o = k0 + ch * ch
+        w2 = params[..., o:o + ch]
+        b0, b1, b2 = params[..., o + ch:o + 2 * ch], params[..., o + 2 * ch:o + 3 * ch], params[..., o + 3 * ch]
+        xs = torch.arange(0, W * stride, stride, dtype=torch.float32, device=feats.device) + stride // 2
+        ys = torch.arange(0, H * stride, stride, dtype=torch.float32, device=feats.device) + stride // 2
+        relx = ref_px[..., 0, None, None] - xs.view(1, 1, 1, W)
+        rely = ref_px[..., 1, None, None] - ys.view(1, 1, H, 1)
+        f = feats.reshape(T, cin, H * W)
+        h1 = torch.einsum("tnok,tkp->tnop", w0[..., 2:], f).view(T, n, ch, H, W)
+        h1 = h1 + w0[..., 0, None, None] * relx[:, :, None] + w0[..., 1, None, None] * rely[:, :, None]
+        h1 = F.relu(h1 + b0[..., None, None]).view(T, n, ch, H * W)
+        h2 = F.relu(torch.einsum("tnok,tnkp->tnop", w1, h1) + b1[..., None])
+        out = torch.einsum("tnk,tnkp->tnp", w2, h2) + b2[..., None]
+        out = self._aligned_bilinear(out.reshape(T * n, 1, H, W), stride // self.mask_stride)
+        return out.view(T, n, out.shape[-2], out.shape[-1])
 
     # ------------------------------------------------------------------ public entry points
     def _flags(self):
