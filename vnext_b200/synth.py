@@ -75,6 +75,9 @@ def fill_state_dict(spec, seed=0):
         if isinstance(v, torch.Tensor) and not v.dtype.is_floating_point:
             out[k] = v.clone()
             continue
+        if isinstance(v, tuple) and len(v) == 2 and v[0] == "index":       # Swin relative_position_index (structural)
+            out[k] = swin_relative_position_index(v[1])
+            continue
         shape = v.shape if isinstance(v, torch.Tensor) else v
         out[k] = fill_tensor(k, shape, seed)
     return out
@@ -100,3 +103,14 @@ def make_msda_inputs(N, Lq, M, D, shapes, P, seed, dtype=torch.float32, loc_rang
     attn = torch.rand(N, Lq, M, L, P, generator=g) + 1e-5
     attn = attn / attn.sum(-1, keepdim=True).sum(-2, keepdim=True)
     return value.to(dtype), shapes_t, lsi, loc.to(dtype), attn.to(dtype)
+
+
+def swin_relative_position_index(ws):
+    """The integer buffer WindowAttention registers (projects/IDOL/idol/backbone/swin.py:108-117)."""
+    coords = torch.stack(torch.meshgrid(torch.arange(ws), torch.arange(ws), indexing="ij"))
+    flat = torch.flatten(coords, 1)
+    rel = (flat[:, :, None] - flat[:, None, :]).permute(1, 2, 0).contiguous()
+    rel[:, :, 0] += ws - 1
+    rel[:, :, 1] += ws - 1
+    rel[:, :, 0] *= 2 * ws - 1
+    return rel.sum(-1)
