@@ -137,7 +137,7 @@ int vnext_msda_backward_host(int dtype, const void *value, const int64_t *spatia
  *          (the reference's value.masked_fill(padding_mask, 0), ms_deform_attn.py:96-97).
  * lda / ldo / ldr / ldb2 are row pitches in elements.  a, weight: 16-byte aligned, lda % 4 == 0, K % 4 == 0 (TMA).
  */
-enum { VNEXT_EPI_RELU = 1, VNEXT_EPI_RESIDUAL = 2, VNEXT_EPI_LAYERNORM = 4 };
+enum { VNEXT_EPI_RELU = 1, VNEXT_EPI_RESIDUAL = 2, VNEXT_EPI_LAYERNORM = 4, VNEXT_EPI_GELU = 8 /* exact erf GELU, applied last */ };
 int vnext_linear_tf32(const float *a, int lda, const float *weight, const float *bias, const float *bias2d,
                       int bias_period, int ldb2, const unsigned char *row_mask, int mask_cols,
                       const float *residual, int ldr, const float *ln_gamma, const float *ln_beta, float ln_eps,
@@ -162,6 +162,22 @@ int vnext_groupnorm_nhwc(const float *x, const float *gamma, const float *beta, 
                          void *stream);
 int vnext_preprocess(int in_is_u8, const void *frames, float *out, int T, int H, int W, int Hp, int Wp,
                      const float *mean3, const float *std3, void *stream);
+
+/*
+ * Swin window attention, one kernel per block (projects/IDOL/idol/backbone/swin.py:129-169 WindowAttention.forward +
+ * the pad / roll / window_partition / window_reverse / roll / crop around it, :252-285):
+ *   qkv   fp32 [B, H, W, 3C]   the block's qkv projection of the UN-padded, UN-rolled norm1(x) (q | k | v, heads x 32 each)
+ *   qkv_bias [3C]              q/k/v of the zero-padded positions (the reference pads after norm1, so they equal the bias)
+ *   rel_pos_bias_table [(2*window-1)^2, heads]
+ *   out   fp32 [B, H, W, C]    softmax(q*scale @ k^T + bias + shift mask) @ v, heads concatenated — the input of `proj`
+ * shift = 0 (W-MSA) or window/2 (SW-MSA; the -100 region mask of BasicLayer.forward :411-438 is generated in-kernel).
+ * Requires C == heads*32 and window <= 12.
+ *   vnext_layernorm: row LayerNorm over C (norm1/norm2, patch-embed / patch-merging / output norms), C % 4 == 0.
+ */
+int vnext_swin_window_attention(const float *qkv, const float *qkv_bias, const float *rel_pos_bias_table, float *out,
+                                int B, int H, int W, int C, int heads, int window, int shift, void *stream);
+int vnext_layernorm(const float *x, const float *gamma, const float *beta, float *out, long long rows, int C,
+                    float eps, void *stream);
 
 /* Which kernel variant the last forward / backward on this thread dispatched to
  * ("fwd_f32_d32_tma", "fwd_generic", ...).  For tests and profiles. */

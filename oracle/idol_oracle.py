@@ -67,11 +67,15 @@ def decoder(sd, tgt, reference_points, memory, shapes, valid_ratios, query_pos, 
 
 
 def inference_forward(sd, frames, pixel_mean=(123.675, 116.280, 103.530), pixel_std=(58.395, 57.120, 57.375),
-                      enc_layers=6, dec_layers=6, return_intermediates=False):
+                      enc_layers=6, dec_layers=6, return_intermediates=False, swin=None):
     """frames: list of N [3,H,W] float tensors (0..255) = the frames of one video, processed as a batch."""
     tensor, mask, image_size = SO.normalize_and_pad(frames, pixel_mean, pixel_std)
     N = tensor.shape[0]
-    feats = SO.resnet50(sd, tensor)
+    if swin is not None:
+        from . import swin_oracle
+        feats = swin_oracle.swin(sd, tensor, SO.BB, **swin)
+    else:
+        feats = SO.resnet50(sd, tensor)
     srcs, masks, poses = [], [], []
     for l, name in enumerate(("res3", "res4", "res5")):
         x = feats[name]

@@ -323,11 +323,15 @@ def dynamic_mask_head(mask_feats, ref_points, params, stride=8, out_stride=4, ch
 
 # ----------------------------------------------------------------------------- full inference
 def inference(sd, frames, pixel_mean=(123.675, 116.280, 103.530), pixel_std=(58.395, 57.120, 57.375),
-              num_queries=None, enc_layers=6, dec_layers=6, return_intermediates=False):
+              num_queries=None, enc_layers=6, dec_layers=6, return_intermediates=False, swin=None):
     """CondInst_segm.inference for ONE video (bs = 1) of T = len(frames) frames."""
     tensor, mask, image_size = normalize_and_pad(frames, pixel_mean, pixel_std)
     T = tensor.shape[0]
-    feats = resnet50(sd, tensor)
+    if swin is not None:          # D2SwinTransformer backbone instead of ResNet-50 (cfg dict, see vnext_b200.swin_spec)
+        from . import swin_oracle
+        feats = swin_oracle.swin(sd, tensor, BB, **swin)
+    else:
+        feats = resnet50(sd, tensor)
     srcs, masks, poses = [], [], []
     for l, name in enumerate(("res3", "res4", "res5")):
         x = feats[name]

@@ -70,3 +70,26 @@ def test_idol_engine_matches_oracle_on_cpu(name):
         out = eng.inference_forward(torch.stack(frames))
     for k, tol in (("pred_logits", 1e-3), ("pred_boxes", 1e-4), ("pred_inst_embed", 1e-3), ("pred_masks", 5e-3)):
         assert torch.allclose(out[k], ref[k], rtol=1e-3, atol=tol), k
+
+
+def test_swin_backbone_host_logic_matches_oracle():
+    """The Swin backbone engine's restructured math (no pad/roll/partition copies; bias-synthesised padded tokens)
+    against the oracle, on CPU (plain-torch formulation of the fused window-attention kernel's contract)."""
+    from oracle import swin_oracle as WO
+    from vnext_b200.swin import SwinBackbone
+    from vnext_b200.swin_spec import swin_state_spec
+
+    class Host:              # the two things the backbone needs from its owning engine
+        native = False
+        lin = staticmethod(lambda x, wb, relu=False, residual=None, ln=None, gelu=False: (
+            lambda y: torch.nn.functional.gelu(y) if gelu else y)(
+            torch.nn.functional.linear(x, wb[0], wb[1]) + (residual if residual is not None else 0)))
+    for cfg, B, H, W, seed in ((dict(embed_dim=96, depths=(2, 2, 2, 2), num_heads=(3, 6, 12, 24), window_size=12), 2, 160, 224, 0),
+                               (dict(embed_dim=64, depths=(2, 2, 2, 2), num_heads=(2, 4, 8, 16), window_size=7), 1, 96, 128, 1)):
+        sd = fill_state_dict(swin_state_spec("bb.", **cfg), seed)
+        x = torch.randn(B, 3, H, W, generator=torch.Generator().manual_seed(seed + 50))
+        with torch.no_grad():
+            want = WO.swin(sd, x, "bb.", **cfg)
+            got = SwinBackbone(sd, "bb.", cfg, torch.device("cpu"), Host).forward(x)
+        for k in want:
+            assert torch.allclose(got[k].permute(0, 3, 1, 2), want[k], rtol=1e-3, atol=2e-4), k

@@ -114,7 +114,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-enum { EPI_RELU = 1, EPI_RESIDUAL = 2, EPI_LAYERNORM = 4 };
+enum { EPI_RELU = 1, EPI_RESIDUAL = 2, EPI_LAYERNORM = 4, EPI_GELU = 8 };
 
 struct GemmParams {
     int M, N, K;
@@ -376,6 +376,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaxf(__uint_as_float(v[j]), 0.f));
                     }
+                    if (p.flags & EPI_GELU) {                            // exact (erf) GELU, nn.GELU's default
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float x = __uint_as_float(v[j]);
+                            v[j] = __float_as_uint(0.5f * x * (1.f + erff(x * 0.70710678118654752f)));
+                        }
+                    }
                     if (masked) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
@@ -563,7 +570,7 @@ extern "C" int vnext_linear_tf32(const float *a, int lda, const float *weight, c
                                  const float *residual, int ldr, const float *ln_gamma, const float *ln_beta,
                                  float ln_eps, float *out, int ldo, int M, int N, int K, int flags, void *stream) {
     VNEXT_CHECK_ARG(M >= 0 && N >= 0 && K > 0, "vnext_linear_tf32: bad sizes M=%d N=%d K=%d", M, N, K);
-    VNEXT_CHECK_ARG(flags >= 0 && flags < 0x800, "vnext_linear_tf32: unknown epilogue flags %d", flags);
+    VNEXT_CHECK_ARG(flags >= 0 && flags < 0x800 && !(flags & 0x0f0), "vnext_linear_tf32: unknown epilogue flags %d", flags);
     if (M == 0 || N == 0) return VNEXT_OK;
     VNEXT_CHECK_ARG(a && weight && out, "vnext_linear_tf32: null pointer");
     VNEXT_CHECK_ARG(al16(a) && al16(weight) && lda % 4 == 0 && K % 4 == 0,

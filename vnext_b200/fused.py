@@ -69,3 +69,29 @@ def preprocess(frames, mean, std, Hp, Wp, out=None):
         ctypes.cast(m, ctypes.c_void_p), ctypes.cast(s, ctypes.c_void_p), _st(frames)))
     _cabi.check(rc, "vnext_preprocess")
     return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    """Row LayerNorm over the last dimension (contiguous rows)."""
+    C = x.shape[-1]
+    assert x.is_contiguous()
+    out = torch.empty_like(x) if out is None else out
+    rows = x.numel() // C
+    rc = _cabi.timed_call("layernorm", {"bytes": 8.0 * x.numel()}, x, lambda: _cabi.lib().vnext_layernorm(
+        x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), rows, C, float(eps), _st(x)))
+    _cabi.check(rc, "vnext_layernorm")
+    return out
+
+
+def swin_window_attention(qkv, qkv_bias, table, heads, window, shift):
+    """qkv [B,H,W,3C] contiguous -> attention output [B,H,W,C] (input of the block's proj Linear)."""
+    B, H, W, C3 = qkv.shape
+    C = C3 // 3
+    assert qkv.is_contiguous() and table.is_contiguous()
+    out = torch.empty((B, H, W, C), dtype=qkv.dtype, device=qkv.device)
+    n = window * window
+    info = {"bytes": 4.0 * (qkv.numel() + out.numel()), "flops": 4.0 * B * (-(-H // window)) * (-(-W // window)) * heads * n * n * 32}
+    rc = _cabi.timed_call("swin_window_attention", info, qkv, lambda: _cabi.lib().vnext_swin_window_attention(
+        qkv.data_ptr(), qkv_bias.data_ptr(), table.data_ptr(), out.data_ptr(), B, H, W, C, heads, window, shift, _st(qkv)))
+    _cabi.check(rc, "vnext_swin_window_attention")
+    return out

@@ -9,7 +9,7 @@ import torch
 
 from . import _cabi
 
-EPI_RELU, EPI_RESIDUAL, EPI_LAYERNORM = 1, 2, 4
+EPI_RELU, EPI_RESIDUAL, EPI_LAYERNORM, EPI_GELU = 1, 2, 4, 8
 
 
 def _ptr(t):
@@ -21,7 +21,7 @@ def _rows(t, n):
     return t2 if t2.stride(-1) == 1 else t2.contiguous()
 
 
-def linear(x, weight, bias=None, relu=False, residual=None, ln_weight=None, ln_bias=None, ln_eps=1e-5, out=None,
+def linear(x, weight, bias=None, relu=False, gelu=False, residual=None, ln_weight=None, ln_bias=None, ln_eps=1e-5, out=None,
            bias2d=None, row_mask=None, mask_cols=0, name=None, _debug_flags=0):
     if not x.is_cuda:
         raise RuntimeError("vnext_b200.linear: CUDA tensors only (no CPU fallback)")
@@ -32,7 +32,7 @@ def linear(x, weight, bias=None, relu=False, residual=None, ln_weight=None, ln_b
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=x.device)
     out2 = out.view(-1, out.shape[-1])[:, :N] if out.shape[-1] != N else out.view(-1, N)
-    flags = (EPI_RELU if relu else 0) | _debug_flags
+    flags = (EPI_RELU if relu else 0) | (EPI_GELU if gelu else 0) | _debug_flags
     res2 = None
     if residual is not None:
         res2 = _rows(residual, N)

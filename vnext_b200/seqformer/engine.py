@@ -79,7 +79,7 @@ def sine_position(mask, num_pos_feats=128, temperature=10000.0):
 class SeqFormerEngine:
     def __init__(self, state_dict, device="cuda", pixel_mean=(123.675, 116.280, 103.530),
                  pixel_std=(58.395, 57.120, 57.375), n_heads=8, n_levels=4, n_points=4, enc_layers=6,
-                 dec_layers=6, mask_stride=4, precision="fp32", msda_impl=None):
+                 dec_layers=6, mask_stride=4, precision="fp32", msda_impl=None, swin=None):
         self.device = torch.device(device)
         self.M, self.L, self.P = n_heads, n_levels, n_points
         self.enc_layers, self.dec_layers = enc_layers, dec_layers
@@ -106,17 +106,22 @@ class SeqFormerEngine:
 
         def cl(w):   # conv weights in channels-last
             return f32(w).contiguous(memory_format=torch.channels_last)
-        bb = packing.pack_resnet50(sd)
-        self.stem = (cl(bb["stem"][0]), f32(bb["stem"][1]))
-        self.stages = []
-        for name, blocks in bb["stages"]:
-            out = []
-            for blk in blocks:
-                o = {"stride": blk["stride"]}
-                for k in ("conv1", "conv2", "conv3", "shortcut"):
-                    o[k] = None if blk[k] is None else (cl(blk[k][0]), f32(blk[k][1]))
-                out.append(o)
-            self.stages.append((name, out))
+        self.swin = None
+        if swin is not None:                       # D2SwinTransformer backbone (cfg dict: vnext_b200.swin_spec.SWIN_L ...)
+            from ..swin import SwinBackbone
+            self.swin = SwinBackbone(sd, packing.BB, swin, dev, self)
+        else:
+            bb = packing.pack_resnet50(sd)
+            self.stem = (cl(bb["stem"][0]), f32(bb["stem"][1]))
+            self.stages = []
+            for name, blocks in bb["stages"]:
+                out = []
+                for blk in blocks:
+                    o = {"stride": blk["stride"]}
+                    for k in ("conv1", "conv2", "conv3", "shortcut"):
+                        o[k] = None if blk[k] is None else (cl(blk[k][0]), f32(blk[k][1]))
+                    out.append(o)
+                self.stages.append((name, out))
         self.input_proj = []
         for l in range(n_levels):
             self.input_proj.append((cl(sd[f"{DETR}input_proj.{l}.0.weight"]), f32(sd[f"{DETR}input_proj.{l}.0.bias"]),
@@ -254,19 +259,21 @@ class SeqFormerEngine:
     def _lin(x, wb):
         return F.linear(x, wb[0], wb[1])
 
-    def lin(self, x, wb, relu=False, residual=None, ln=None, **kw):
+    def lin(self, x, wb, relu=False, residual=None, ln=None, gelu=False, **kw):
         """y = [relu]( [LayerNorm]( x W^T + b [+ residual] ) ) — one tcgen05 kernel when native."""
         if self.native_gemm:
             from ..linear import linear
             if residual is not None and residual.shape != x.shape[:-1] + (wb[0].shape[0],):
                 residual = residual.expand(*x.shape[:-1], wb[0].shape[0])
-            return linear(x, wb[0], wb[1], relu=relu, residual=residual, ln_weight=None if ln is None else ln[0],
-                          ln_bias=None if ln is None else ln[1], **kw)
+            return linear(x, wb[0], wb[1], relu=relu, gelu=gelu, residual=residual,
+                          ln_weight=None if ln is None else ln[0], ln_bias=None if ln is None else ln[1], **kw)
         y = F.linear(x, wb[0], wb[1])
         if residual is not None:
             y = y + residual
         if ln is not None:
             y = F.layer_norm(y, (y.shape[-1],), ln[0], ln[1], 1e-5)
+        if gelu:
+            y = F.gelu(y)
         return F.relu(y) if relu else y
 
     def _mha(self, q_in, v_in, w, residual=None, ln=None):
@@ -344,6 +351,9 @@ class SeqFormerEngine:
         return X
 
     def backbone(self, x):
+        if self.swin is not None:                  # channels-last features; non-native callers expect NCHW
+            feats = self.swin.forward(x)
+            return feats if self.native else {k: v.permute(0, 3, 1, 2) for k, v in feats.items()}
         if self.native:
             return self.backbone_native(x)
         x = self._conv(x, self.stem, stride=2, padding=3, relu=True)

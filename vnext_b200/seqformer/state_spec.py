@@ -60,8 +60,15 @@ def _mha(spec, p, C):
     _linear(spec, p + ".out_proj", C, C)
 
 
-def seqformer_r50_state_spec(num_queries=300, num_classes=40, C=256, ffn=1024, M=8, L=4, P=4, enc=6, dec=6):
-    spec = resnet50_spec("detr.detr.backbone.0.backbone.")
+def seqformer_r50_state_spec(num_queries=300, num_classes=40, C=256, ffn=1024, M=8, L=4, P=4, enc=6, dec=6, swin=None):
+    """swin: None for ResNet-50, else a Swin cfg dict (vnext_b200.swin_spec.SWIN_L ...)."""
+    if swin is None:
+        spec = resnet50_spec("detr.detr.backbone.0.backbone.")
+        in_ch = (512, 1024, 2048)
+    else:
+        from ..swin_spec import swin_state_spec
+        spec = swin_state_spec("detr.detr.backbone.0.backbone.", **swin)
+        in_ch = tuple(swin["embed_dim"] * 2 ** i for i in (1, 2, 3))
     T = "detr.detr.transformer."
     for i in range(enc):
         p = f"{T}encoder.layers.{i}"
@@ -99,7 +106,7 @@ def seqformer_r50_state_spec(num_queries=300, num_classes=40, C=256, ffn=1024, M
         for j, (co, ci) in enumerate(((C, C), (C, C), (4, C))):
             _linear(spec, f"{D}bbox_embed.{i}.layers.{j}", co, ci)
     spec[D + "query_embed.weight"] = (num_queries, 2 * C)
-    for l, (cin, k) in enumerate(((512, 1), (1024, 1), (2048, 1), (2048, 3))):
+    for l, (cin, k) in enumerate(((in_ch[0], 1), (in_ch[1], 1), (in_ch[2], 1), (in_ch[2], 3))):
         spec[f"{D}input_proj.{l}.0.weight"] = (C, cin, k, k)
         spec[f"{D}input_proj.{l}.0.bias"] = (C,)
         spec[f"{D}input_proj.{l}.1.weight"] = (C,)
