@@ -24,7 +24,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-WORKLOADS = {"720p": (5, 720, 1280), "480p": (5, 480, 864)}
+WORKLOADS = {"720p": (5, 720, 1280), "480p": (5, 480, 864), "swinl_720p": (5, 720, 1280)}
 METRIC = "frames/sec SeqFormer-R50 T=5 720p synthetic"
 
 
@@ -89,10 +89,10 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
-def make_weights(seed=0):
+def make_weights(seed=0, swin=None):
     from vnext_b200.seqformer.state_spec import seqformer_r50_state_spec
     from vnext_b200.synth import fill_state_dict
-    return fill_state_dict(seqformer_r50_state_spec(), seed)
+    return fill_state_dict(seqformer_r50_state_spec(swin=swin), seed)
 
 
 def make_clip_u8(T, H, W, seed=0):
@@ -159,7 +159,14 @@ def own_arm(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     T, H, W = WORKLOADS[args.workload]
-    model = SeqFormer(state_dict=make_weights(0), device=str(dev), precision=args.precision).eval()
+    swin = None
+    if args.workload.startswith("swinl"):           # BASELINE config 4's backbone (tf32 here; bf16 is a later round)
+        from vnext_b200.swin_spec import SWIN_L
+        swin = dict(SWIN_L)
+    model = SeqFormer(device=str(dev), precision=args.precision)
+    model.swin = swin
+    model.load_reference_state_dict(make_weights(0, swin))
+    model.eval()
     clip = make_clip_u8(T, H, W, rank)
     run = model.runner(T, H, W, (H, W))                    # captures the CUDA graph
     run.frames_dev.copy_(clip.to(dev))
@@ -242,12 +249,13 @@ def own_arm(args, rank, world, local_rank):
                                 "us_per_step": round(m["us"] / 3, 1)}
 
     cpu = None
-    if args.gpus == 1 and not args.no_cpu_baseline:
+    if args.gpus == 1 and not args.no_cpu_baseline and swin is None:
         cfps, desc, cores, _ = cpu_oracle_fps(T, H, W, 1, 0, budget_s=20.0)
         cpu = {"value": round(cfps, 4), "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc}
 
     line = {
-        "metric": METRIC if args.workload == "720p" else METRIC.replace("720p", "480x864"),
+        "metric": {"720p": METRIC, "480p": METRIC.replace("720p", "480x864"),
+                   "swinl_720p": METRIC.replace("R50", "SwinL")}[args.workload],
         "value": round(fps, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else args.precision, "data": "synthetic",

@@ -31,6 +31,12 @@ class SeqFormer(nn.Module):
         self.pixel_std = tuple(g("MODEL.PIXEL_STD", (58.395, 57.120, 57.375)))
         self.device_name = g("MODEL.DEVICE", device)
         self.precision = precision
+        # backbone: build_resnet_backbone (R50) or D2SwinTransformer (cfg.MODEL.SWIN.*, S/config.py:67-83)
+        self.swin = None
+        if g("MODEL.BACKBONE.NAME", "build_resnet_backbone") == "D2SwinTransformer":
+            self.swin = dict(embed_dim=g("MODEL.SWIN.EMBED_DIM", 96), depths=tuple(g("MODEL.SWIN.DEPTHS", (2, 2, 6, 2))),
+                             num_heads=tuple(g("MODEL.SWIN.NUM_HEADS", (3, 6, 12, 24))),
+                             window_size=g("MODEL.SWIN.WINDOW_SIZE", 7))
         self.__dict__.update(overrides)
         self.engine = None
         self._runners = {}
@@ -38,7 +44,7 @@ class SeqFormer(nn.Module):
             self.load_reference_state_dict(state_dict)
 
     def expected_state_spec(self):
-        return seqformer_r50_state_spec(self.num_queries, self.num_classes)
+        return seqformer_r50_state_spec(self.num_queries, self.num_classes, swin=self.swin)
 
     def load_reference_state_dict(self, state_dict):
         """Takes a reference-layout checkpoint (`model` dict of a DetectionCheckpointer .pth)."""
@@ -51,7 +57,7 @@ class SeqFormer(nn.Module):
                 raise ValueError(f"{k}: expected shape {tuple(shp)}, got {tuple(state_dict[k].shape)}")
         self.engine = SeqFormerEngine(state_dict, device=self.device_name, pixel_mean=self.pixel_mean,
                                       pixel_std=self.pixel_std, mask_stride=self.mask_stride,
-                                      precision=self.precision)
+                                      precision=self.precision, swin=self.swin)
         self._runners = {}
 
     def runner(self, T, H, W, ori_size):
