@@ -53,6 +53,8 @@ class SeqFormer(nn.Module):
         if missing:
             raise KeyError(f"checkpoint is missing {len(missing)} keys, e.g. {missing[:3]}")
         for k, shp in spec.items():
+            if shp and shp[0] == "index":              # structural integer buffer (Swin relative_position_index)
+                shp = (shp[1] ** 2, shp[1] ** 2)
             if tuple(state_dict[k].shape) != tuple(shp):
                 raise ValueError(f"{k}: expected shape {tuple(shp)}, got {tuple(state_dict[k].shape)}")
         self.engine = SeqFormerEngine(state_dict, device=self.device_name, pixel_mean=self.pixel_mean,
