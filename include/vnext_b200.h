@@ -144,6 +144,17 @@ int vnext_linear_tf32(const float *a, int lda, const float *weight, const float 
                       float *out, int ldo, int M, int N, int K, int flags, void *stream);
 
 /*
+ * 3x3 convolution, stride 1, zero padding 1, NHWC fp32, as an implicit GEMM on the tcgen05 tensor cores (TF32) with
+ * the folded-FrozenBN bias and ReLU fused: out[T,H,W,Cout] = act(conv3x3(x[T,H,W,Cin]) + bias).  Replaces the cuDNN
+ * conv + BN-affine + ReLU passes of BottleneckBlock.conv2 (detectron2/modeling/backbone/resnet.py:150-161, 194-199)
+ * and of MaskHeadSmallConv (projects/SeqFormer/seqformer/models/segmentation_condInst.py:539-575).
+ * weight_khwc: the conv weight re-laid at load time as [Cout, 3, 3, Cin] (K index = (ky*3 + kx)*Cin + c).
+ * Needs Cin % 32 == 0, Cout % 4 == 0.  No im2col buffer: every filter tap is a shifted 4-D TMA box of the input.
+ */
+int vnext_conv3x3_tf32(const float *x, const float *weight_khwc, const float *bias, float *out, int T, int H, int W,
+                       int Cin, int Cout, int relu, void *stream);
+
+/*
  * Single-pass NHWC epilogues of the backbone / input projection (fp32, C % 4 == 0, 16-byte aligned):
  *   vnext_bias_act      out = act(x + bias[c] (+ residual))      — folded FrozenBN bias + ReLU (+ shortcut) after a
  *                       library conv (detectron2/modeling/backbone/resnet.py:194-210; layers/batch_norm.py:44-65)

@@ -81,3 +81,20 @@ def test_residual_relu_bias2d_and_row_mask():
     want[mask.bool().repeat(M // S).cpu().cuda(), :256] = 0
     assert (out.double() - want).abs().max().item() < tol
     assert (out[mask.bool().repeat(M // S), :256] == 0).all()
+
+
+@pytest.mark.parametrize("T,H,W,Cin,Cout", [(2, 23, 40, 64, 64), (1, 8, 16, 32, 128), (3, 46, 80, 256, 256),
+                                           (1, 184, 320, 64, 64), (2, 13, 17, 128, 8), (5, 92, 160, 256, 64)])
+def test_conv3x3_implicit_gemm(T, H, W, Cin, Cout):
+    from vnext_b200.linear import conv3x3
+    g = torch.Generator().manual_seed(T * 1000 + H)
+    x = torch.randn(T, H, W, Cin, generator=g).cuda()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5).cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), padding=1).permute(0, 2, 3, 1)
+    out = conv3x3(x, wk, b, relu=False)
+    tol = 2e-3 * ref.abs().max().item()
+    assert (out.double() - ref).abs().max().item() < tol
+    out = conv3x3(x, wk, b, relu=True)
+    assert (out.double() - ref.clamp(min=0)).abs().max().item() < tol

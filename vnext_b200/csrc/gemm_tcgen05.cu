@@ -32,6 +32,19 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *t
         "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, int c2, int c3,
+                                            uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *tmap, const void *smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tmap),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
 // shared -> global tile store (TMA); rows / columns beyond the tensor extent are clipped by the hardware
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *tmap, const void *smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),
@@ -133,6 +146,10 @@ struct GemmParams {
     int tma_epi;             // epilogue tiles go through shared memory + TMA (coalesced); else direct row stores
     float eps;
     int num_m_tiles, num_n_tiles;
+    // implicit-GEMM 3x3 convolution (stride 1, zero padding 1) over NHWC: the A tile of an 8 x 16 pixel patch and filter
+    // tap (ky, kx) is ONE 4-D TMA box at (channel block, x0 + kx - 1, y0 + ky - 1, frame); out-of-image pixels are
+    // zero-filled by the TMA unit, which is exactly the convolution's padding
+    int conv, conv_cin_blocks, conv_tiles_x, conv_tiles_y;
 };
 
 constexpr int kGemmThreads = 384;      // warps 0-3: TMA / MMA / TMEM-alloc / idle; warps 4-11: epilogue
@@ -189,7 +206,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     unsigned char *const epi_smem = smem + STAGES * STAGE_BYTES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+    const int num_k_blocks = p.conv ? 9 * p.conv_cin_blocks : (p.K + BLOCK_K - 1) / BLOCK_K;
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
 
     if (warp == 0 && lane == 0) {
@@ -234,7 +251,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 unsigned char *sa = smem + stage * STAGE_BYTES, *sb = sa + A_BYTES;
                 mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-                tma_load_2d(sa, &tmap_a, kb * BLOCK_K, m_idx, &full_bar[stage]);
+                if (p.conv) {
+                    const int mt = tile / p.num_n_tiles;
+                    const int tx = mt % p.conv_tiles_x, ty = (mt / p.conv_tiles_x) % p.conv_tiles_y;
+                    const int fr = mt / (p.conv_tiles_x * p.conv_tiles_y);
+                    const int tap = kb / p.conv_cin_blocks, cb = kb - tap * p.conv_cin_blocks;
+                    tma_load_4d(sa, &tmap_a, cb * BLOCK_K, tx * 16 + tap % 3 - 1, ty * 8 + tap / 3 - 1, fr, &full_bar[stage]);
+                } else {
+                    tma_load_2d(sa, &tmap_a, kb * BLOCK_K, m_idx, &full_bar[stage]);
+                }
                 tma_load_2d(sb, &tmap_b, kb * BLOCK_K, n_idx, &full_bar[stage]);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
@@ -406,7 +431,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         fence_proxy_async();
                         __syncwarp();
                         if (lane == 0) {
-                            tma_store_2d(&tmap_out, ob, col0, row0);
+                            if (p.conv) {     // this warp's 32 tile rows = 2 image rows x 16 pixels of the 8 x 16 patch
+                                const int mt = tile / p.num_n_tiles;
+                                const int tx = mt % p.conv_tiles_x, ty = (mt / p.conv_tiles_x) % p.conv_tiles_y;
+                                tma_store_4d(&tmap_out, ob, col0, tx * 16, ty * 8 + 2 * ew, mt / (p.conv_tiles_x * p.conv_tiles_y));
+                            } else {
+                                tma_store_2d(&tmap_out, ob, col0, row0);
+                            }
                             tma_store_commit();
                         }
                         ++stores;
@@ -490,6 +521,27 @@ static int make_tmap_f32(CUtensorMap *tm, const float *ptr, int rows, int cols, 
     return VNEXT_OK;
 }
 
+// 4-D fp32 NHWC tensor [T, H, W, C]; box = [1, box_h, box_w, 32 channels], SWIZZLE_128B
+static int make_tmap_nhwc(CUtensorMap *tm, const float *ptr, int T, int H, int W, int C, int box_h, int box_w) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return VNEXT_ECUDA;
+    }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    cuuint32_t box[4] = {32u, (cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
+    cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (NHWC) failed (%d) for [%d,%d,%d,%d]", (int)r, T, H, W, C);
+        return VNEXT_ECUDA;
+    }
+    return VNEXT_OK;
+}
+
 template <int BLOCK_N, int STAGES>
 static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &to, const CUtensorMap &tr,
                        GemmParams p, cudaStream_t stream) {
@@ -500,7 +552,7 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUten
         VNEXT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    p.num_m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+    if (!p.conv) p.num_m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
     p.num_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -531,6 +583,7 @@ int linear_tf32_device(const LinearArgs &x, cudaStream_t stream) {
     p.ldb2 = x.ldb2; p.row_mask = x.row_mask; p.mask_cols = x.mask_cols; p.residual = x.residual; p.gamma = x.gamma;
     p.beta = x.beta; p.out = x.out; p.ldo = x.ldo; p.ldr = x.ldr; p.flags = x.flags; p.eps = x.eps;
     p.num_m_tiles = p.num_n_tiles = 0;
+    p.conv = p.conv_cin_blocks = p.conv_tiles_x = p.conv_tiles_y = 0;
     p.vec_ok = al16(x.out) && x.ldo % 4 == 0 && (!x.bias || al16(x.bias)) &&
                (!x.bias2d || (al16(x.bias2d) && x.ldb2 % 4 == 0)) && (!x.residual || (al16(x.residual) && x.ldr % 4 == 0));
     const bool wide = (x.N % 256 == 0);
@@ -561,9 +614,41 @@ int linear_tf32_device(const LinearArgs &x, cudaStream_t stream) {
     return wide ? launch_gemm<256, 3>(ta, tb, to, tr, p, stream) : launch_gemm<128, 4>(ta, tb, to, tr, p, stream);
 }
 
+int conv3x3_tf32_device(const float *x, const float *w, const float *bias, float *out, int T, int H, int W, int Cin,
+                        int Cout, int relu, cudaStream_t stream) {
+    GemmParams p;
+    p.M = T * H * W; p.N = Cout; p.K = 9 * Cin; p.bias = bias; p.bias2d = nullptr; p.period = 1; p.ldb2 = 0;
+    p.row_mask = nullptr; p.mask_cols = 0; p.residual = nullptr; p.gamma = p.beta = nullptr; p.out = out; p.ldo = Cout;
+    p.ldr = 0; p.flags = relu ? EPI_RELU : 0; p.eps = 0.f; p.vec_ok = 1; p.tma_epi = 1;
+    p.conv = 1; p.conv_cin_blocks = Cin / 32; p.conv_tiles_x = (W + 15) / 16; p.conv_tiles_y = (H + 7) / 8;
+    p.num_m_tiles = T * p.conv_tiles_x * p.conv_tiles_y;
+    p.num_n_tiles = 0;
+    const bool wide = (Cout % 256 == 0);
+    CUtensorMap ta, tb, to;
+    int rc = make_tmap_nhwc(&ta, x, T, H, W, Cin, 8, 16);
+    if (rc) return rc;
+    rc = make_tmap_f32(&tb, w, Cout, 9 * Cin, 9 * Cin, wide ? 256 : 128);
+    if (rc) return rc;
+    rc = make_tmap_nhwc(&to, out, T, H, W, Cout, 2, 16);
+    if (rc) return rc;
+    return wide ? launch_gemm<256, 3>(ta, tb, to, to, p, stream) : launch_gemm<128, 4>(ta, tb, to, to, p, stream);
+}
+
 }  // namespace vnext
 
 using namespace vnext;
+
+extern "C" int vnext_conv3x3_tf32(const float *x, const float *weight_khwc, const float *bias, float *out, int T, int H,
+                                  int W, int Cin, int Cout, int relu, void *stream) {
+    VNEXT_CHECK_ARG(T >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "vnext_conv3x3_tf32: bad shape");
+    VNEXT_CHECK_ARG(Cin % 32 == 0 && Cout % 4 == 0, "vnext_conv3x3_tf32: needs Cin %% 32 == 0 and Cout %% 4 == 0 (got %d, %d)",
+                    Cin, Cout);
+    if (T == 0) return VNEXT_OK;
+    VNEXT_CHECK_ARG(x && weight_khwc && out && al16(x) && al16(weight_khwc) && al16(out) && (!bias || al16(bias)),
+                    "vnext_conv3x3_tf32: null or unaligned pointer");
+    VNEXT_CHECK_ARG((long long)T * H * W < (1ll << 31), "vnext_conv3x3_tf32: too many pixels");
+    return conv3x3_tf32_device(x, weight_khwc, bias, out, T, H, W, Cin, Cout, relu, static_cast<cudaStream_t>(stream));
+}
 
 extern "C" int vnext_linear_tf32(const float *a, int lda, const float *weight, const float *bias, const float *bias2d,
                                  int bias_period, int ldb2, const unsigned char *row_mask, int mask_cols,

@@ -56,3 +56,18 @@ def linear(x, weight, bias=None, relu=False, gelu=False, residual=None, ln_weigh
                 out2.stride(0), M, N, K, flags, torch.cuda.current_stream(x.device).cuda_stream))
     _cabi.check(rc, "vnext_linear_tf32")
     return out2.view(*x.shape[:-1], N) if out2.is_contiguous() else out2
+
+
+def conv3x3(x, weight_khwc, bias, relu=True):
+    """x [T,H,W,Cin] contiguous NHWC; weight_khwc [Cout, 9*Cin] (= conv weight.permute(0,2,3,1)); stride 1, padding 1."""
+    T, H, W, Cin = x.shape
+    Cout = weight_khwc.shape[0]
+    assert x.is_contiguous() and weight_khwc.is_contiguous()
+    out = torch.empty((T, H, W, Cout), dtype=torch.float32, device=x.device)
+    info = {"flops": 2.0 * T * H * W * Cout * 9 * Cin, "bytes": 4.0 * (x.numel() + out.numel() + weight_khwc.numel())}
+    with torch.cuda.device(x.device):
+        rc = _cabi.timed_call(f"conv3x3_tf32_c{Cin}_n{Cout}", info, x, lambda: _cabi.lib().vnext_conv3x3_tf32(
+            x.data_ptr(), weight_khwc.data_ptr(), _ptr(bias), out.data_ptr(), T, H, W, Cin, Cout, int(relu),
+            torch.cuda.current_stream(x.device).cuda_stream))
+    _cabi.check(rc, "vnext_conv3x3_tf32")
+    return out
