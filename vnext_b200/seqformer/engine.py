@@ -95,6 +95,7 @@ class SeqFormerEngine:
         # engine with the GEMMs on cuBLAS fp32 — the strict 1e-3 parity mode of the tests.
         self.native_gemm = self.native and precision != "fp32"
         self._plans: Dict[Tuple[int, int, int], ClipPlan] = {}
+        self._khwc = {}
         sd = state_dict
         dev = self.device
         f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
@@ -305,8 +306,17 @@ class SeqFormerEngine:
         return x.contiguous(memory_format=torch.channels_last)
 
     def _conv3x3_native(self, x_nhwc, wb, stride=1, relu=True):
-        """3x3 conv on the library (cuDNN, no bias) + ONE fused bias/ReLU pass.  x_nhwc: [T,h,w,C] contiguous."""
+        """3x3 conv + folded-BN bias + ReLU.  Stride 1 with Cin % 32 == 0: implicit GEMM on tcgen05 (shifted 4-D TMA
+        boxes, fused epilogue).  Otherwise (the three stride-2 convs, fp32 parity mode): library conv without bias +
+        ONE fused bias/ReLU pass.  x_nhwc: [T,h,w,C] contiguous."""
         from .. import fused
+        cin, cout = wb[0].shape[1], wb[0].shape[0]
+        if self.native_gemm and stride == 1 and cin % 32 == 0 and cout % 4 == 0:
+            from ..linear import conv3x3
+            key = wb[0].data_ptr()
+            if key not in self._khwc:              # [Cout, Cin, 3, 3] -> [Cout, (ky, kx, c)], once per weight
+                self._khwc[key] = wb[0].permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
+            return conv3x3(x_nhwc.contiguous(), self._khwc[key], wb[1], relu=relu)
         y = F.conv2d(x_nhwc.permute(0, 3, 1, 2), wb[0], None, stride=stride, padding=1).permute(0, 2, 3, 1)
         return fused.bias_act(y, wb[1], relu=relu, out=y)
 
