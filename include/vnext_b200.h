@@ -190,6 +190,22 @@ int vnext_swin_window_attention(const float *qkv, const float *qkv_bias, const f
 int vnext_layernorm(const float *x, const float *gamma, const float *beta, float *out, long long rows, int C,
                     float eps, void *stream);
 
+/*
+ * CondInst dynamic mask head + video-level mask post-processing.
+ *   vnext_dynamic_mask_head: logits8[n, T, H, W] = MLP_i([ref_i - loc(x, y) | feats[t, y, x, 0:8]]) with the 10->8->8->1
+ *     per-instance MLP generated by the controller (169 parameters: w0[8x10] w1[8x8] w2[8] b0[8] b1[8] b2, i.e.
+ *     parse_dynamic_params' order, segmentation_condInst.py:614-637).  mask_feats [T, H, W, 8] NHWC; params [n, 169]
+ *     shared by all frames (SeqFormer) or [T, n, 169] when params_per_frame != 0 (IDOL); ref_px [T, n, 2] = (x, y) in
+ *     pixels; loc(x, y) = (x, y) * feat_stride + feat_stride / 2 (compute_locations :665-678).  Replaces
+ *     dynamic_mask_with_coords / mask_heads_forward (:404-493) up to, not including, aligned_bilinear.
+ *   vnext_mask_finalize: boolean masks out[n_images, OH, OW] (uint8 0/1) = nearest_resize(crop_{H,W}(sigmoid(
+ *     bilinear_x{mask_stride}(aligned_bilinear_x2(logits8))))) > 0.5 — seqformer.py:381-396 + segmentation_condInst.py:640-662.
+ */
+int vnext_dynamic_mask_head(const float *mask_feats, const float *params, int params_per_frame, const float *ref_px,
+                            float *out, int T, int n_inst, int H, int W, int feat_stride, void *stream);
+int vnext_mask_finalize(const float *logits8, unsigned char *out, int n_images, int H8, int W8, int H, int W, int OH,
+                        int OW, int mask_stride, void *stream);
+
 /* Which kernel variant the last forward / backward on this thread dispatched to
  * ("fwd_f32_d32_tma", "fwd_generic", ...).  For tests and profiles. */
 const char *vnext_msda_last_variant(void);

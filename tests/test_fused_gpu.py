@@ -54,3 +54,34 @@ def test_preprocess(dtype):
     want = F.pad((fr.float() - m) / s, (0, 16, 0, 16)).permute(0, 2, 3, 1)
     assert torch.allclose(out, want, rtol=1e-6, atol=1e-6)
     assert (out[:, 80:] == 0).all() and (out[:, :, 112:] == 0).all()
+
+
+@pytest.mark.parametrize("per_frame", [False, True])
+def test_dynamic_mask_head_kernel(per_frame):
+    from oracle import seqformer_oracle as SO
+    from vnext_b200 import fused
+    g = torch.Generator().manual_seed(7)
+    T, n, H, W = 3, 13, 23, 40
+    feats = torch.randn(T, H, W, 8, generator=g)
+    params = torch.randn((T, n, 169) if per_frame else (n, 169), generator=g) * 0.3
+    ref = torch.rand(T, n, 2, generator=g) * torch.tensor([W * 8.0, H * 8.0])
+    got = fused.dynamic_mask_head(feats.cuda(), params.cuda(), ref.cuda(), 8).cpu()          # [n, T, H, W]
+    for t in range(T):
+        prm = params[t] if per_frame else params
+        want = SO.dynamic_mask_head(feats[t:t + 1].permute(0, 3, 1, 2), ref[t:t + 1], prm[None], out_stride=8)  # no upsample
+        assert torch.allclose(got[:, t], want[0], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("H,W,OH,OW", [(720, 1280, 720, 1280), (80, 112, 80, 112), (96, 128, 60, 80), (90, 120, 180, 250)])
+def test_mask_finalize_kernel(H, W, OH, OW):
+    from oracle import seqformer_oracle as SO
+    from vnext_b200 import fused
+    g = torch.Generator().manual_seed(H + OW)
+    Hp, Wp = (H + 31) // 32 * 32, (W + 31) // 32 * 32
+    l8 = torch.randn(4, 2, Hp // 8, Wp // 8, generator=g) * 3
+    got = fused.mask_finalize(l8.cuda(), (H, W), (OH, OW), 4).cpu()
+    m4 = SO.aligned_bilinear(l8.reshape(8, 1, Hp // 8, Wp // 8), 2).view(4, 2, Hp // 4, Wp // 4)
+    pm = F.interpolate(m4, size=(Hp, Wp), mode="bilinear", align_corners=False).sigmoid()[:, :, :H, :W]
+    want = F.interpolate(pm, size=(OH, OW), mode="nearest") > 0.5
+    assert got.dtype == torch.bool and got.shape == want.shape
+    assert (got == want).float().mean().item() > 0.9995

@@ -20,5 +20,5 @@ with _cabi.KernelTimer() as kt:
     for _ in range(3):
         eng.infer_video_device(frames, (H, W))
 agg = kt.summary()
-for name, d in sorted(agg.items(), key=lambda kv: -kv[1]["us"])[:8]:
+for name, d in sorted(agg.items(), key=lambda kv: -kv[1]["us"])[:int(os.environ.get("TOPN", "8"))]:
     print(f"{name:34s} calls/step {d['calls'] // 3:3d}  avg {d['us'] / d['calls']:8.1f} us  {d['bytes'] / d['us'] / 1e3:8.1f} GB/s")

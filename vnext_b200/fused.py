@@ -95,3 +95,32 @@ def swin_window_attention(qkv, qkv_bias, table, heads, window, shift):
         qkv.data_ptr(), qkv_bias.data_ptr(), table.data_ptr(), out.data_ptr(), B, H, W, C, heads, window, shift, _st(qkv)))
     _cabi.check(rc, "vnext_swin_window_attention")
     return out
+
+
+def dynamic_mask_head(feats_nhwc, params, ref_px, stride=8):
+    """feats_nhwc [T,H,W,8]; params [n,169] or [T,n,169]; ref_px [T,n,2] -> stride-8 logits [n,T,H,W]."""
+    T, H, W, C = feats_nhwc.shape
+    assert C == 8 and feats_nhwc.is_contiguous()
+    per_frame = params.dim() == 3
+    n = params.shape[-2]
+    params, ref_px = params.contiguous(), ref_px.contiguous()
+    out = torch.empty((n, T, H, W), dtype=torch.float32, device=feats_nhwc.device)
+    info = {"bytes": 4.0 * (out.numel() + feats_nhwc.numel()), "flops": 304.0 * out.numel()}
+    rc = _cabi.timed_call("dynamic_mask_head", info, feats_nhwc, lambda: _cabi.lib().vnext_dynamic_mask_head(
+        feats_nhwc.data_ptr(), params.data_ptr(), int(per_frame), ref_px.data_ptr(), out.data_ptr(), T, n, H, W, stride,
+        _st(feats_nhwc)))
+    _cabi.check(rc, "vnext_dynamic_mask_head")
+    return out
+
+
+def mask_finalize(logits8, frame_hw, out_hw, mask_stride=4):
+    """logits8 [n,T,H8,W8] -> bool masks [n,T,OH,OW] (upsample x2 aligned, x mask_stride bilinear, sigmoid, crop, resize, >0.5)."""
+    n, T, H8, W8 = logits8.shape
+    assert logits8.is_contiguous()
+    out = torch.empty((n, T, out_hw[0], out_hw[1]), dtype=torch.uint8, device=logits8.device)
+    info = {"bytes": float(out.numel() + 4 * logits8.numel())}
+    rc = _cabi.timed_call("mask_finalize", info, logits8, lambda: _cabi.lib().vnext_mask_finalize(
+        logits8.data_ptr(), out.data_ptr(), n * T, H8, W8, frame_hw[0], frame_hw[1], out_hw[0], out_hw[1], mask_stride,
+        _st(logits8)))
+    _cabi.check(rc, "vnext_mask_finalize")
+    return out.view(torch.bool)

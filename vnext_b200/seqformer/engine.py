@@ -514,6 +514,12 @@ class SeqFormerEngine:
         feats [T, 8, H, W]; params [n, 169]; ref_px [T, n, 2]  ->  [n, T, 2H, 2W]
         (segmentation_condInst.py:404-493 without materialising the [1, n*10, H, W] tensor)."""
         T, cin, H, W = feats.shape
+        if self.native:                             # fused per-instance MLP kernel (no [n*10, H, W] tensor, no einsums)
+            l8 = self.mask_logits8(feats, params, ref_px, stride)                       # [n, T, H, W]
+            n = l8.shape[0]
+            up = self._aligned_bilinear(l8.reshape(n * T, 1, H, W), stride // self.mask_stride)
+            up = up.view(n, T, up.shape[-2], up.shape[-1])
+            return up.transpose(0, 1) if params.dim() == 3 else up
         if params.dim() == 3:                       # IDOL: every frame has its own instance parameters
             return self._dynamic_masks_per_frame(feats, params, ref_px, stride)
         n = params.shape[0]
@@ -535,6 +541,11 @@ class SeqFormerEngine:
         out = torch.einsum("nk,tnkp->tnp", w2, h2) + b2[None, :, None]
         out = self._aligned_bilinear(out.reshape(T * n, 1, H, W), stride // self.mask_stride)
         return out.view(T, n, out.shape[-2], out.shape[-1]).transpose(0, 1)
+
+    def mask_logits8(self, feats, params, ref_px, stride=8):
+        """Stride-8 instance mask logits [n, T, H, W] from the fused kernel (feats: [T, 8, H, W] view of NHWC memory)."""
+        from .. import fused
+        return fused.dynamic_mask_head(feats.permute(0, 2, 3, 1).contiguous(), params, ref_px, stride)
 
     def _dynamic_masks_per_frame(self, feats, params, ref_px, stride=8):
         """params [T, n, 169]; ref_px [T, n, 2] -> [T, n, 2H, 2W]."""
@@ -599,6 +610,10 @@ class SeqFormerEngine:
         k = min(topk, scores.shape[0])
         _, idx = torch.topk(scores.max(1)[0], k=k)
         feats = self.mask_features(memory, plan)
+        if self.native:      # stride-8 logits -> boolean output masks in one pass (no stride-4 / full-res float tensors)
+            from .. import fused
+            l8 = self.mask_logits8(feats, params[idx], ref_px[:, idx])
+            return scores[idx], fused.mask_finalize(l8, (H, W), tuple(ori_size), self.mask_stride)
         m = self.dynamic_masks(feats, params[idx], ref_px[:, idx])               # [k, T, H/4, W/4]
         oh, ow = m.shape[-2:]
         pm = F.interpolate(m, size=(oh * self.mask_stride, ow * self.mask_stride), mode="bilinear",
