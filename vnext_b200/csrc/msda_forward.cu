@@ -127,7 +127,7 @@ __device__ __forceinline__ float transpose_reduce(float (&a)[VEC], int lane) {
 }
 
 template <typename VT, int LK, bool FUSED>
-__global__ void __launch_bounds__(kFwdThreads, 6) msda_fwd_tile_kernel(const MsdaFwdParams p) {
+__global__ void __launch_bounds__(kFwdThreads, 8) msda_fwd_tile_kernel(const MsdaFwdParams p) {
     using RV = RowVec<VT>;
     constexpr int VEC = RV::VEC, LPC = RV::LPC, NG = 32 / LPC;
     constexpr int PPP = 32 / LK;         // pairs per 32-sample warp pass
@@ -360,8 +360,8 @@ static int launch_tile(const MsdaFwdParams &p0, cudaStream_t stream) {
     if (FUSED) {   // whole projection rows per tile: TP must be a multiple of M
         while (min_tp % p.M != 0) min_tp += kFwdWarps * PPP;
     }
-    int tp = 64;
-    if (FUSED) tp = ((64 + p.M - 1) / p.M) * p.M;
+    int tp = 32;          // 2 stages x 6 KB staging + 8.6 KB static: 8 CTAs (32 warps) per SM
+    if (FUSED) tp = ((32 + p.M - 1) / p.M) * p.M;
     while (tp / 2 >= min_tp && (tp / 2) % min_tp == 0 && (p.pairs + tp - 1) / tp < 8 * num_sms()) tp >>= 1;
     if (tp < min_tp || tp % min_tp != 0) tp = min_tp;
     p.TP = tp;
