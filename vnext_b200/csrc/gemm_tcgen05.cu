@@ -19,6 +19,8 @@
 //   * persistent grid, static round-robin over (m, n) tiles, n fastest so neighbouring CTAs share A in L2.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vnext {
@@ -31,6 +33,30 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *t
             smem_u32(smem_dst)),
         "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+// 2-CTA cluster helpers: one CTA's TMA load lands in the shared memory of every CTA in `mask` (same offset) and
+// signals each one's mbarrier; tcgen05.commit can likewise arrive on the same barrier in every CTA of the mask.
+__device__ __forceinline__ void tma_load_2d_mcast(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, uint64_t *bar,
+                                                  uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+        "[%2], %5;" ::"r"(smem_u32(smem_dst)),
+        "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
 }
 __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, int c2, int c3,
                                             uint64_t *bar) {
@@ -150,6 +176,9 @@ struct GemmParams {
     // tap (ky, kx) is ONE 4-D TMA box at (channel block, x0 + kx - 1, y0 + ky - 1, frame); out-of-image pixels are
     // zero-filled by the TMA unit, which is exactly the convolution's padding
     int conv, conv_cin_blocks, conv_tiles_x, conv_tiles_y;
+    // cluster == 2: CTA pairs work on two vertically adjacent m-tiles of the same n-tile; each CTA loads half of the
+    // weight (B) tile and multicasts it to both, halving the dominant L2 -> shared-memory operand traffic
+    int cluster;
 };
 
 constexpr int kGemmThreads = 384;      // warps 0-3: TMA / MMA / TMEM-alloc / idle; warps 4-11: epilogue
@@ -207,7 +236,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k_blocks = p.conv ? 9 * p.conv_cin_blocks : (p.K + BLOCK_K - 1) / BLOCK_K;
-    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    // work distribution: a work item is one output tile (cluster 1) or a vertical pair of tiles (cluster 2)
+    const int csize = p.cluster;
+    const uint32_t crank = csize > 1 ? cluster_ctarank() : 0u;
+    const int first_work = blockIdx.x / csize, work_stride = gridDim.x / csize;
+    const int num_work = ((p.num_m_tiles + csize - 1) / csize) * p.num_n_tiles;
+    auto work_tile = [&](int w) { return ((w / p.num_n_tiles) * csize + (int)crank) * p.num_n_tiles + w % p.num_n_tiles; };
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_a);
@@ -217,7 +251,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], csize);
         }
 #pragma unroll
         for (int s = 0; s < ACC_STAGES; ++s) {
@@ -234,17 +268,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (csize > 1) cluster_sync_all();          // peers' barriers are initialised before anything remote touches them
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
     if (warp == 0 && lane == 0) {
         // ===================== TMA producer =====================
         int stage = 0, phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int work = first_work; work < num_work; work += work_stride) {
+            const int tile = work_tile(work);
             const int m_idx = (tile / p.num_n_tiles) * BLOCK_M, n_idx = (tile % p.num_n_tiles) * BLOCK_N;
-            // every CTA walks K from a different starting block: all SMs want the same weight tile at about the
-            // same time, and starting them at different k spreads those requests over the L2 slices
-            const int k_rot = (int)(blockIdx.x % (unsigned)num_k_blocks);
+            // every CTA (pair) walks K from a different starting block: all SMs want the same weight tile at about
+            // the same time, and starting them at different k spreads those requests over the L2 slices
+            const int k_rot = (int)((unsigned)first_work % (unsigned)num_k_blocks);
             for (int kb0 = 0; kb0 < num_k_blocks; ++kb0) {
                 int kb = kb0 + k_rot;
                 if (kb >= num_k_blocks) kb -= num_k_blocks;
@@ -260,14 +296,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 } else {
                     tma_load_2d(sa, &tmap_a, kb * BLOCK_K, m_idx, &full_bar[stage]);
                 }
-                tma_load_2d(sb, &tmap_b, kb * BLOCK_K, n_idx, &full_bar[stage]);
+                if (csize > 1)      // my half of the weight tile, delivered to both CTAs of the pair
+                    tma_load_2d_mcast(sb + crank * (B_BYTES / 2), &tmap_b, kb * BLOCK_K, n_idx + (int)crank * (BLOCK_N / 2),
+                                      &full_bar[stage], (uint16_t)3);
+                else
+                    tma_load_2d(sb, &tmap_b, kb * BLOCK_K, n_idx, &full_bar[stage]);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1 && lane == 0) {
         // ===================== MMA issuer =====================
         int stage = 0, phase = 0, acc = 0, acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int work = first_work; work < num_work; work += work_stride) {
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -279,7 +319,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                 for (int k = 0; k < BLOCK_K / UMMA_K; ++k)   // advance 32 B inside the 128-B swizzle row: +2 in 16-B units
                     umma<0>(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0);
-                umma_commit(&empty_bar[stage]);
+                if (csize > 1) umma_commit_mcast(&empty_bar[stage], (uint16_t)3);   // frees the slot in BOTH CTAs
+                else umma_commit(&empty_bar[stage]);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
             umma_commit(&tmem_full[acc]);
@@ -306,7 +347,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             prefetch_tmap(&tmap_out);
             if (has_res) prefetch_tmap(&tmap_res);
         }
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int work = first_work; work < num_work; work += work_stride) {
+            const int tile = work_tile(work);
             const int m_idx = (tile / p.num_n_tiles) * BLOCK_M, n_idx = (tile % p.num_n_tiles) * BLOCK_N;
             const int row0 = m_idx + ew * 32;
             const int row = row0 + lane;
@@ -476,6 +518,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (csize > 1) cluster_sync_all();          // nobody leaves while a peer may still multicast into it / arrive on its barriers
     if (warp == 2) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
@@ -555,7 +598,24 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUten
     if (!p.conv) p.num_m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
     p.num_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
     const int tiles = p.num_m_tiles * p.num_n_tiles;
-    const int grid = tiles < num_sms() ? tiles : num_sms();
+    int grid = tiles < num_sms() ? tiles : num_sms();
+    if (p.cluster == 2) {
+        const int pairs = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+        grid = 2 * (pairs < num_sms() / 2 ? pairs : num_sms() / 2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kGemmThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        VNEXT_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tr, p));
+        count_launch();
+        return VNEXT_OK;
+    }
     kern<<<grid, kGemmThreads, smem, stream>>>(ta, tb, to, tr, p);
     count_launch();
     VNEXT_CUDA(cudaGetLastError());
@@ -584,6 +644,7 @@ int linear_tf32_device(const LinearArgs &x, cudaStream_t stream) {
     p.beta = x.beta; p.out = x.out; p.ldo = x.ldo; p.ldr = x.ldr; p.flags = x.flags; p.eps = x.eps;
     p.num_m_tiles = p.num_n_tiles = 0;
     p.conv = p.conv_cin_blocks = p.conv_tiles_x = p.conv_tiles_y = 0;
+    p.cluster = 1;
     p.vec_ok = al16(x.out) && x.ldo % 4 == 0 && (!x.bias || al16(x.bias)) &&
                (!x.bias2d || (al16(x.bias2d) && x.ldb2 % 4 == 0)) && (!x.residual || (al16(x.residual) && x.ldr % 4 == 0));
     const bool wide = (x.N % 256 == 0);
@@ -596,7 +657,13 @@ int linear_tf32_device(const LinearArgs &x, cudaStream_t stream) {
     CUtensorMap ta, tb, to, tr;
     int rc = make_tmap_f32(&ta, x.a, x.M, x.K, x.lda, BLOCK_M);
     if (rc) return rc;
-    rc = make_tmap_f32(&tb, x.w, x.N, x.K, x.K, wide ? 256 : 128);
+    {   // pair CTAs (weight-tile multicast) whenever there are enough m-tiles to keep every SM busy in pairs
+        static const char *env = getenv("VNEXT_GEMM_CLUSTER");
+        const int want = env ? atoi(env) : 1;      // measured: no gain (these GEMMs are HBM-bound, not operand-bound) -> off
+        const int m_tiles = (x.M + BLOCK_M - 1) / BLOCK_M;
+        if (want == 2 && m_tiles * ((x.N + (wide ? 255 : 127)) / (wide ? 256 : 128)) >= 2 * num_sms()) p.cluster = 2;
+    }
+    rc = make_tmap_f32(&tb, x.w, x.N, x.K, x.K, (wide ? 256 : 128) / p.cluster);
     if (rc) return rc;
     // coalesced epilogue through shared memory + TMA needs 16-byte aligned rows of out (and residual)
     p.tma_epi = al16(x.out) && x.ldo % 4 == 0 && (!x.residual || (al16(x.residual) && x.ldr % 4 == 0));
@@ -623,11 +690,17 @@ int conv3x3_tf32_device(const float *x, const float *w, const float *bias, float
     p.conv = 1; p.conv_cin_blocks = Cin / 32; p.conv_tiles_x = (W + 15) / 16; p.conv_tiles_y = (H + 7) / 8;
     p.num_m_tiles = T * p.conv_tiles_x * p.conv_tiles_y;
     p.num_n_tiles = 0;
+    p.cluster = 1;
     const bool wide = (Cout % 256 == 0);
+    {
+        static const char *env = getenv("VNEXT_GEMM_CLUSTER");
+        const int want = env ? atoi(env) : 1;
+        if (want == 2 && p.num_m_tiles * ((Cout + (wide ? 255 : 127)) / (wide ? 256 : 128)) >= 2 * num_sms()) p.cluster = 2;
+    }
     CUtensorMap ta, tb, to;
     int rc = make_tmap_nhwc(&ta, x, T, H, W, Cin, 8, 16);
     if (rc) return rc;
-    rc = make_tmap_f32(&tb, w, Cout, 9 * Cin, 9 * Cin, wide ? 256 : 128);
+    rc = make_tmap_f32(&tb, w, Cout, 9 * Cin, 9 * Cin, (wide ? 256 : 128) / p.cluster);
     if (rc) return rc;
     rc = make_tmap_nhwc(&to, out, T, H, W, Cout, 2, 16);
     if (rc) return rc;
