@@ -294,3 +294,17 @@ def test_fused_frontend_vs_oracle(ops, N, Lq, M, L, K, shared, ref_dim):
     got2 = ops.ms_deform_attn_fused(value.cuda(), shapes_t.cuda(), lsi.cuda(), wide.cuda()[..., :oa.shape[-1]],
                                     ref.cuda(), L, K)
     assert torch.equal(got2, got)
+
+
+def test_backward_large_lk32_regression(ops):
+    """L*K = 32 with enough pairs to pick the largest tile (shared-memory sizing of the backward tile kernel)."""
+    shapes = [(13, 9), (7, 5), (4, 3), (2, 2)]
+    value, shapes_t, lsi, loc, attn = O.make_inputs(8, 1000, 8, 32, shapes, 8, 77, loc_range=(-0.1, 1.1))
+    gout = torch.rand(8, 1000, 256, generator=torch.Generator().manual_seed(3))
+    gv, gl, ga = ops.ms_deform_attn_backward(*_cuda(value, shapes_t, lsi, loc, attn, gout), 64)
+    assert _variant() == "bwd_f32_d32_tma"
+    idx = torch.arange(0, 1000, 97)
+    cv, cl, ca = O.backward_c(value, shapes_t, lsi, loc[:, idx].contiguous(), attn[:, idx].contiguous(),
+                              gout[:, idx].contiguous(), np.float64)
+    assert torch.allclose(gl.cpu()[:, idx].double(), cl, rtol=1e-3, atol=1e-5)
+    assert torch.allclose(ga.cpu()[:, idx].double(), ca, rtol=1e-3, atol=1e-6)

@@ -295,6 +295,7 @@ static int launch_bwd_tile(const MsdaBwdParams &p0, cudaStream_t stream) {
     const int min_tp = kBwdWarps * PPP;
     int tp = 64;
     while (tp > min_tp && (p.pairs + tp - 1) / tp < 8 * num_sms()) tp >>= 1;
+    while (tp > min_tp && (size_t)kBwdStages * tp * LK * 12 > 40 * 1024) tp >>= 1;   // stay under the 48 KB default with the static part
     if (tp < min_tp) tp = min_tp;
     p.TP = tp;
     p.num_tiles = (p.pairs + tp - 1) / tp;
