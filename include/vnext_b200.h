@@ -187,6 +187,9 @@ int vnext_preprocess(int in_is_u8, const void *frames, float *out, int T, int H,
  */
 int vnext_swin_window_attention(const float *qkv, const float *qkv_bias, const float *rel_pos_bias_table, float *out,
                                 int B, int H, int W, int C, int heads, int window, int shift, void *stream);
+/* Same contract on the tcgen05 tensor cores (TF32 MMAs, S / P / O in TMEM, per-thread row softmax); window in [4, 12]. */
+int vnext_swin_window_attention_tc(const float *qkv, const float *qkv_bias, const float *rel_pos_bias_table, float *out,
+                                   int B, int H, int W, int C, int heads, int window, int shift, void *stream);
 int vnext_layernorm(const float *x, const float *gamma, const float *beta, float *out, long long rows, int C,
                     float eps, void *stream);
 

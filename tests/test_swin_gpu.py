@@ -32,6 +32,9 @@ def test_window_attention_kernel(B, H, W, heads, ws, shift):
     want = _window_attention_torch(qkv.double(), bias.double(), table.double(), heads, ws, shift)
     got = fused.swin_window_attention(qkv, bias, table, heads, ws, shift)
     assert (got.double() - want).abs().max().item() < 2e-5
+    if ws >= 4:           # tensor-core (TF32) variant: same contract, TF32 tolerance
+        tc = fused.swin_window_attention(qkv, bias, table, heads, ws, shift, tensor_cores=True)
+        assert (tc.double() - want).abs().max().item() < 5e-3 * max(1.0, want.abs().max().item())
 
 
 def test_layernorm_and_gelu_epilogue():

@@ -83,15 +83,17 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
     return out
 
 
-def swin_window_attention(qkv, qkv_bias, table, heads, window, shift):
-    """qkv [B,H,W,3C] contiguous -> attention output [B,H,W,C] (input of the block's proj Linear)."""
+def swin_window_attention(qkv, qkv_bias, table, heads, window, shift, tensor_cores=False):
+    """qkv [B,H,W,3C] contiguous -> attention output [B,H,W,C] (input of the block's proj Linear).
+    tensor_cores: tcgen05 TF32 kernel (csrc/swin_attention_tc.cu) instead of the exact-fp32 SIMT kernel."""
     B, H, W, C3 = qkv.shape
     C = C3 // 3
     assert qkv.is_contiguous() and table.is_contiguous()
     out = torch.empty((B, H, W, C), dtype=qkv.dtype, device=qkv.device)
     n = window * window
     info = {"bytes": 4.0 * (qkv.numel() + out.numel()), "flops": 4.0 * B * (-(-H // window)) * (-(-W // window)) * heads * n * n * 32}
-    rc = _cabi.timed_call("swin_window_attention", info, qkv, lambda: _cabi.lib().vnext_swin_window_attention(
+    fn = _cabi.lib().vnext_swin_window_attention_tc if (tensor_cores and window >= 4) else _cabi.lib().vnext_swin_window_attention
+    rc = _cabi.timed_call("swin_window_attention_tc" if (tensor_cores and window >= 4) else "swin_window_attention", info, qkv, lambda: fn(
         qkv.data_ptr(), qkv_bias.data_ptr(), table.data_ptr(), out.data_ptr(), B, H, W, C, heads, window, shift, _st(qkv)))
     _cabi.check(rc, "vnext_swin_window_attention")
     return out

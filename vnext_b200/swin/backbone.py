@@ -50,7 +50,8 @@ class SwinBackbone:
         ws = self.cfg["window_size"]
         if self.eng.native:
             from .. import fused
-            return fused.swin_window_attention(qkv.contiguous(), blk["qkv"][1], blk["table"], blk["heads"], ws, blk["shift"])
+            return fused.swin_window_attention(qkv.contiguous(), blk["qkv"][1], blk["table"], blk["heads"], ws, blk["shift"],
+                                               tensor_cores=getattr(self.eng, "native_gemm", False))
         return _window_attention_torch(qkv, blk["qkv"][1], blk["table"], blk["heads"], ws, blk["shift"])
 
     def forward(self, x):
