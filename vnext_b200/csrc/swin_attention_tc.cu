@@ -128,7 +128,9 @@ __global__ void __launch_bounds__(kTcThreads, 2) swin_window_attention_tc_kernel
             stok[t] = (y < p.H && x < p.W) ? ((b * p.H + y) * p.W + x) : -1;
             const int hr = ys < p.Hp - ws ? 0 : (ys < p.Hp - p.shift ? 1 : 2);
             const int wr = xs < p.Wp - ws ? 0 : (xs < p.Wp - p.shift ? 1 : 2);
-            sreg[t] = p.shift > 0 ? hr * 3 + wr : 0;
+            // packed per-token code: bias-table offset of the token as a KEY ((t / ws) * (2ws-1) + t % ws) and its shift
+            // region, so the softmax loop needs no integer division
+            sreg[t] = (((t / ws) * (2 * ws - 1) + t % ws) << 4) | (p.shift > 0 ? hr * 3 + wr : 0);
         }
         for (int i = tid; i < (2 * ws - 1) * (2 * ws - 1); i += kTcThreads) sbias[i] = p.table[(size_t)i * p.heads + h];
         __syncthreads();
@@ -169,42 +171,49 @@ __global__ void __launch_bounds__(kTcThreads, 2) swin_window_attention_tc_kernel
             parity ^= 1;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-            // ---- softmax of this thread's row (TMEM lane == row)
+            // ---- softmax of this thread's row (TMEM lane == row).  Warps whose 32 rows are all padding skip it.
             const int i = mb * 128 + tid;
-            const int ic = min(i, N - 1);
-            const int iy = ic / ws, ix = ic % ws, ireg = sreg[ic];
-            float mx = -INFINITY;
-            for (int c0 = 0; c0 < NK; c0 += 16) {
-                uint32_t v[16];
-                tc_ld16(lane_addr + c0, v);
+            const bool warp_live = mb * 128 + warp * 32 < N;
+            float sum = 1.f;
+            if (warp_live) {
+                const int ic = min(i, N - 1);
+                const int icode = sreg[ic];
+                const int ireg = icode & 15;
+                // bias index = (iy - jy + ws-1)*(2ws-1) + (ix - jx + ws-1) = key_i - key_j + (ws-1)*(2ws-1) + (ws-1)
+                const int ibase = (icode >> 4) + (ws - 1) * (2 * ws - 1) + (ws - 1);
+                float mx = -INFINITY;
+                for (int c0 = 0; c0 < NK; c0 += 16) {
+                    uint32_t v[16];
+                    tc_ld16(lane_addr + c0, v);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int col = c0 + j;
-                    float s = -INFINITY;
-                    if (col < N) {
-                        const int jy = col / ws, jx = col % ws;
-                        s = __uint_as_float(v[j]) + sbias[(iy - jy + ws - 1) * (2 * ws - 1) + (ix - jx + ws - 1)];
-                        if (sreg[col] != ireg) s += -100.0f;
+                    for (int j = 0; j < 16; ++j) {
+                        const int col = c0 + j;
+                        float s = -INFINITY;
+                        if (col < N) {
+                            const int jc = sreg[col];
+                            s = __uint_as_float(v[j]) + sbias[ibase - (jc >> 4)];
+                            if ((jc & 15) != ireg) s += -100.0f;
+                        }
+                        mx = fmaxf(mx, s);
+                        v[j] = __float_as_uint(s);
                     }
-                    mx = fmaxf(mx, s);
-                    v[j] = __float_as_uint(s);
+                    tc_st16(lane_addr + c0, v);
                 }
-                tc_st16(lane_addr + c0, v);
-            }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            float sum = 0.f;
-            for (int c0 = 0; c0 < NK; c0 += 16) {
-                uint32_t v[16];
-                tc_ld16(lane_addr + c0, v);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                sum = 0.f;
+                for (int c0 = 0; c0 < NK; c0 += 16) {
+                    uint32_t v[16];
+                    tc_ld16(lane_addr + c0, v);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float e = expf(__uint_as_float(v[j]) - mx);      // exp(-inf) = 0 for the padding columns
-                    sum += e;
-                    v[j] = __float_as_uint(e);
+                    for (int j = 0; j < 16; ++j) {
+                        const float e = __expf(__uint_as_float(v[j]) - mx);    // exp(-inf) = 0 for the padding columns
+                        sum += e;
+                        v[j] = __float_as_uint(e);
+                    }
+                    tc_st16(lane_addr + c0, v);
                 }
-                tc_st16(lane_addr + c0, v);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncthreads();
 
@@ -223,7 +232,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) swin_window_attention_tc_kernel
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
             // ---- epilogue: O / sum -> out[token]
-            {
+            if (warp_live) {
                 uint32_t v[16];
                 const float inv = 1.f / sum;
                 const int tok = i < N ? stok[i] : -1;
