@@ -194,6 +194,17 @@ int vnext_layernorm(const float *x, const float *gamma, const float *beta, float
                     float eps, void *stream);
 
 /*
+ * Fused AdamW over a flat fp32 segment (training step; torch.optim.AdamW semantics as built by
+ * projects/IDOL/train_net.py:94-140, gradient clipping :110-125 folded into *grad_scale):
+ *   g' = g * (*grad_scale);  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;
+ *   w = w (1 - lr wd) - lr / bias_correction1 * m / (sqrt(v) / sqrt(bias_correction2) + eps)
+ * n % 4 == 0, 16-byte aligned device buffers; grad_scale is a DEVICE pointer to one float (NULL = 1).
+ */
+int vnext_adamw(float *w, const float *g, float *m, float *v, long long n, float lr, float beta1, float beta2,
+                float eps, float weight_decay, float bias_correction1, float bias_correction2, const float *grad_scale,
+                void *stream);
+
+/*
  * CondInst dynamic mask head + video-level mask post-processing.
  *   vnext_dynamic_mask_head: logits8[n, T, H, W] = MLP_i([ref_i - loc(x, y) | feats[t, y, x, 0:8]]) with the 10->8->8->1
  *     per-instance MLP generated by the controller (169 parameters: w0[8x10] w1[8x8] w2[8] b0[8] b1[8] b2, i.e.

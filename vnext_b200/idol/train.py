@@ -1,0 +1,430 @@
+"""IDOL training step (SURVEY §8d cfg 3): the dense forward of `CondInst_segm.forward(..., train=True)`
+(projects/IDOL/idol/models/segmentation_condInst.py:77-231) on a reference-layout state dict, differentiable, with
+every multi-scale deformable attention (6 encoder + 6 decoder layers, key and reference frames) going through this
+repo's sm_100a forward/backward kernels (`vnext_b200.msda.MSDeformAttnFunction`, C ABI vnext_msda_forward/backward).
+
+What runs where this round:
+  * MSDA forward + backward .................. hand-written kernels (csrc/msda_forward.cu, csrc/msda_backward.cu)
+  * AdamW over the flat parameter buffer ..... hand-written kernel (csrc/optimizer.cu, C ABI vnext_adamw)
+  * convolutions / linears and their grads ... cuDNN / cuBLAS through torch autograd (the reference's own training
+    path; replacing their dgrad/wgrad with tcgen05 kernels is next-round work)
+  * losses, simOTA, contrastive selection .... host Python/PyTorch (criterion.py), as the north star prescribes
+  * gradient exchange ........................ ONE all-reduce of the flat gradient buffer (NCCL over NVLink)
+
+B200-first structure rather than the reference's: key and reference frames go through backbone + transformer as ONE
+batch (the reference runs the transformer twice, segm:140-141; samples are independent so values are identical);
+FrozenBN is folded into the conv weights on the fly (no per-conv affine pass over the activations); the mask branch
+is evaluated once per step, not once per decoder level (segm:190, identical values, gradients accumulate); all
+trainable parameters and their gradients live in two flat fp32 buffers (parameters are views), so gradient averaging
+is one collective and the optimiser is one launch per learning-rate group.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .. import _cabi
+from ..msda import MSDeformAttnFunction
+from . import criterion as crit
+from .state_spec import idol_r50_state_spec
+
+BB = "detr.detr.backbone.0.backbone."
+DETR = "detr.detr."
+TR = "detr.detr.transformer."
+ALIAS = TR + "decoder.bbox_embed."            # same Parameters as detr.detr.bbox_embed.* (deformable_detr.py:101-104)
+
+
+def inverse_sigmoid(x, eps=1e-5):
+    x = x.clamp(min=0, max=1)
+    return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
+
+
+def _is_frozen(key, freeze_at):
+    if not key.startswith(BB):
+        return False
+    if ".norm." in key:                         # FrozenBatchNorm2d: all four tensors are buffers (batch_norm.py:36-42)
+        return True
+    stage = key[len(BB):].split(".")[0]                     # FREEZE_AT=k freezes stem and res2..res(k) (resnet.py:613-650)
+    return stage in (["stem"] + [f"res{i}" for i in range(2, 6)])[:freeze_at]
+
+
+class FlatParams:
+    """Trainable tensors as views into one fp32 buffer per role (weights, grads, Adam moments), grouped by learning
+    rate: group 0 = backbone (BASE_LR x BACKBONE_MULTIPLIER, train_net.py:104-108), group 1 = everything else."""
+
+    ALIGN = 64
+
+    def __init__(self, tensors, device):
+        keys = sorted(tensors, key=lambda k: (0 if "backbone" in k else 1, k))
+        self.offsets, n = {}, 0
+        self.group_end = [0, 0]
+        for k in keys:
+            self.offsets[k] = (n, tensors[k].numel(), tuple(tensors[k].shape))
+            n += (tensors[k].numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+            self.group_end[0 if "backbone" in k else 1] = n
+        if self.group_end[1] < self.group_end[0]:
+            self.group_end[1] = self.group_end[0]
+        self.numel = n
+        self.w = torch.zeros(n, dtype=torch.float32, device=device)
+        self.g = torch.zeros_like(self.w)
+        self.m = torch.zeros_like(self.w)
+        self.v = torch.zeros_like(self.w)
+        self.params = {}
+        for k in keys:
+            o, cnt, shape = self.offsets[k]
+            self.w[o:o + cnt].copy_(tensors[k].reshape(-1).to(device=device, dtype=torch.float32))
+            p = nn.Parameter(self.w[o:o + cnt].view(shape))
+            p.grad = self.g[o:o + cnt].view(shape)          # autograd accumulates in place into the flat buffer
+            self.params[k] = p
+
+    def groups(self):
+        return [(0, self.group_end[0]), (self.group_end[0], self.group_end[1])]
+
+
+def adamw_(w, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale):
+    """One fused AdamW update of a flat fp32 segment (C ABI vnext_adamw; torch.optim.AdamW semantics).  `grad_scale`
+    is a 1-element device tensor (clip coefficient / world size) so no host sync sits between backward and update."""
+    if not w.is_cuda:
+        raise RuntimeError("vnext_adamw: Not implemented on the CPU")
+    if w.numel() == 0:
+        return
+    rc = _cabi.lib().vnext_adamw(w.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), w.numel(), float(lr),
+                                 float(beta1), float(beta2), float(eps), float(weight_decay),
+                                 float(1.0 - beta1 ** step), float(1.0 - beta2 ** step), grad_scale.data_ptr(),
+                                 torch.cuda.current_stream(w.device).cuda_stream)
+    _cabi.check(rc, "vnext_adamw")
+
+
+class IDOLTrainModel(nn.Module):
+    def __init__(self, state_dict, device="cuda", num_classes=40, num_queries=300, dropout=0.1, freeze_at=2,
+                 pixel_mean=(123.675, 116.280, 103.530), pixel_std=(58.395, 57.120, 57.375), mask_stride=4,
+                 weight_dict=None, heads=8, levels=4, points=4):
+        super().__init__()
+        self.device = torch.device(device)
+        spec = idol_r50_state_spec(num_queries, num_classes)
+        missing = [k for k in spec if k not in state_dict]
+        if missing:
+            raise KeyError(f"checkpoint is missing {len(missing)} keys, e.g. {missing[:3]}")
+        train, self.frozen = {}, {}
+        for k in spec:
+            if k.startswith(ALIAS):
+                continue
+            t = state_dict[k].detach()
+            if _is_frozen(k, freeze_at):
+                self.frozen[k] = t.to(self.device, torch.float32)
+            else:
+                train[k] = t
+        self.flat = FlatParams(train, self.device)
+        self._plist = nn.ParameterList(list(self.flat.params.values()))     # module bookkeeping (.parameters())
+        self.P = dict(self.frozen)
+        self.P.update(self.flat.params)
+        self.dropout, self.M, self.L, self.K = dropout, heads, levels, points
+        self.num_classes, self.mask_stride = num_classes, mask_stride
+        self.mean = torch.tensor(pixel_mean, device=self.device).view(1, 3, 1, 1)
+        self.std = torch.tensor(pixel_std, device=self.device).view(1, 3, 1, 1)
+        self.weight_dict = weight_dict or crit.default_weight_dict()
+        self.criterion = crit.SetCriterion(num_classes, self.weight_dict, mask_out_stride=mask_stride)
+        self.enc_layers = 1 + max(int(k.split(".")[5]) for k in spec if k.startswith(TR + "encoder.layers."))
+        self.dec_layers = 1 + max(int(k.split(".")[5]) for k in spec if k.startswith(TR + "decoder.layers."))
+
+    # ------------------------------------------------------------------ state dict in the reference's layout
+    def reference_state_dict(self):
+        out = {k: v.detach().clone() for k, v in self.P.items()}
+        for k in list(out):
+            if k.startswith(DETR + "bbox_embed."):
+                out[ALIAS + k[len(DETR + "bbox_embed."):]] = out[k]
+        return out
+
+    # ------------------------------------------------------------------ small helpers
+    def _drop(self, x):
+        return F.dropout(x, self.dropout, self.training) if self.dropout > 0 else x
+
+    def _lin(self, p, x):
+        return F.linear(x, self.P[p + ".weight"], self.P[p + ".bias"])
+
+    def _ln(self, p, x):
+        return F.layer_norm(x, (x.shape[-1],), self.P[p + ".weight"], self.P[p + ".bias"], 1e-5)
+
+    def _mlp(self, p, x, n=3):
+        for i in range(n):
+            x = self._lin(f"{p}.layers.{i}", x)
+            if i < n - 1:
+                x = F.relu(x)
+        return x
+
+    def _conv_bn(self, p, x, stride=1, padding=0, relu=True):
+        n = p + ".norm."
+        scale = self.P[n + "weight"] * torch.rsqrt(self.P[n + "running_var"] + 1e-5)      # batch_norm.py:48-53
+        shift = self.P[n + "bias"] - self.P[n + "running_mean"] * scale
+        x = F.conv2d(x, self.P[p + ".weight"] * scale.view(-1, 1, 1, 1), shift, stride=stride, padding=padding)
+        return F.relu(x, inplace=True) if relu else x
+
+    # ------------------------------------------------------------------ backbone (resnet.py:194-210, 355-359, 435-458)
+    def backbone(self, x):
+        out = {}
+        with torch.no_grad():
+            x = self._conv_bn(BB + "stem.conv1", x, stride=2, padding=3)
+            x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+        for stage, nblocks in (("res2", 3), ("res3", 4), ("res4", 6), ("res5", 3)):
+            for b in range(nblocks):
+                p = f"{BB}{stage}.{b}."
+                stride = 2 if (b == 0 and stage != "res2") else 1
+                y = self._conv_bn(p + "conv1", x)
+                y = self._conv_bn(p + "conv2", y, stride=stride, padding=1)
+                y = self._conv_bn(p + "conv3", y, relu=False)
+                sc = self._conv_bn(p + "shortcut", x, stride=stride, relu=False) if (p + "shortcut.weight") in self.P \
+                    else x
+                x = F.relu(y + sc)
+            out[stage] = x
+        return out
+
+    @staticmethod
+    def _sine_pos(mask, num_pos_feats=128, temperature=10000.0):
+        """position_encoding.py:36-56 (normalize=True)."""
+        nm = ~mask
+        y, x = nm.cumsum(1, dtype=torch.float32), nm.cumsum(2, dtype=torch.float32)
+        y = (y - 0.5) / (y[:, -1:, :] + 1e-6) * (2 * math.pi)
+        x = (x - 0.5) / (x[:, :, -1:] + 1e-6) * (2 * math.pi)
+        d = torch.arange(num_pos_feats, dtype=torch.float32, device=mask.device)
+        d = temperature ** (2 * (d // 2) / num_pos_feats)
+        px, py = x[..., None] / d, y[..., None] / d
+        px = torch.stack((px[..., 0::2].sin(), px[..., 1::2].cos()), 4).flatten(3)
+        py = torch.stack((py[..., 0::2].sin(), py[..., 1::2].cos()), 4).flatten(3)
+        return torch.cat((py, px), 3)                                           # [N, h, w, 256] (token-major)
+
+    # ------------------------------------------------------------------ MSDeformAttn module (ops/modules/ms_deform_attn.py:78-116)
+    def _msda(self, p, query, ref, src, shapes, lsi, pad_mask):
+        N, Lq, C = query.shape
+        M, L, K = self.M, self.L, self.K
+        v = self._lin(p + ".value_proj", src)
+        if pad_mask is not None:
+            v = v.masked_fill(pad_mask[..., None], 0.0)
+        n_off = M * L * K * 2
+        w = torch.cat([self.P[p + ".sampling_offsets.weight"], self.P[p + ".attention_weights.weight"]], 0)
+        b = torch.cat([self.P[p + ".sampling_offsets.bias"], self.P[p + ".attention_weights.bias"]], 0)
+        oa = F.linear(query, w, b)                                              # one pass over the queries for both
+        off = oa[..., :n_off].reshape(N, Lq, M, L, K, 2)
+        aw = torch.softmax(oa[..., n_off:].reshape(N, Lq, M, L * K), -1).view(N, Lq, M, L, K)
+        if ref.shape[-1] == 2:
+            norm = torch.stack([shapes[..., 1], shapes[..., 0]], -1).to(off.dtype)
+            loc = ref[:, :, None, :, None, :] + off / norm[None, None, None, :, None, :]
+        else:
+            loc = ref[:, :, None, :, None, :2] + off / K * ref[:, :, None, :, None, 2:] * 0.5
+        out = MSDeformAttnFunction.apply(v.view(N, -1, M, C // M), shapes, lsi, loc.contiguous(), aw.contiguous(), 64)
+        return self._lin(p + ".output_proj", out)
+
+    def _mha(self, p, q_in, v_in):
+        """nn.MultiheadAttention(q=k=q_in, v=v_in) of the decoder self-attention (deformable_transformer.py:306-313)."""
+        C = q_in.shape[-1]
+        w, b = self.P[p + ".in_proj_weight"], self.P[p + ".in_proj_bias"]
+        qk = F.linear(q_in, w[:2 * C], b[:2 * C])
+        v = F.linear(v_in, w[2 * C:], b[2 * C:])
+        B, Lq, _ = qk.shape
+        d = C // self.M
+        q = qk[..., :C].reshape(B, Lq, self.M, d).transpose(1, 2)
+        k = qk[..., C:].reshape(B, Lq, self.M, d).transpose(1, 2)
+        v = v.reshape(B, Lq, self.M, d).transpose(1, 2)
+        o = F.scaled_dot_product_attention(q, k, v, dropout_p=self.dropout if self.training else 0.0)
+        return F.linear(o.transpose(1, 2).reshape(B, Lq, C), self.P[p + ".out_proj.weight"], self.P[p + ".out_proj.bias"])
+
+    # ------------------------------------------------------------------ dense forward over all frames
+    def dense(self, frames):
+        """frames [N,3,H,W] float 0..255 (N = 2 x videos: key, ref, key, ref ...), all of one size.
+        -> dict(hs [dec,N,nq,C], memory [N,S,C], init_ref [N,nq,2], inter_ref [dec,N,nq,4], shapes, lsi, image_size)"""
+        N, _, H, W = frames.shape
+        Hp, Wp = (H + 31) // 32 * 32, (W + 31) // 32 * 32
+        x = (frames.to(self.device, torch.float32) - self.mean) / self.std
+        x = F.pad(x, (0, Wp - W, 0, Hp - H))
+        mask = torch.ones(N, Hp, Wp, dtype=torch.bool, device=self.device)
+        mask[:, :H, :W] = False
+        feats = self.backbone(x)
+        srcs, masks, poses = [], [], []
+        for l, name in enumerate(("res3", "res4", "res5", "res5")):
+            k = 3 if l == 3 else 1
+            s = F.conv2d(feats[name], self.P[f"{DETR}input_proj.{l}.0.weight"], self.P[f"{DETR}input_proj.{l}.0.bias"],
+                         stride=2 if l == 3 else 1, padding=k // 2)
+            s = F.group_norm(s, 32, self.P[f"{DETR}input_proj.{l}.1.weight"], self.P[f"{DETR}input_proj.{l}.1.bias"], 1e-5)
+            with torch.no_grad():
+                # level masks: nearest-resized padding mask; level 3 resizes masks[0] (segm:117-118)
+                m = F.interpolate((mask if l < 3 else masks[0])[None].float(), size=s.shape[-2:]).to(torch.bool)[0]
+                pos = self._sine_pos(m).flatten(1, 2)
+            srcs.append(s.flatten(2).transpose(1, 2))
+            masks.append(m)
+            poses.append(pos + self.P[TR + "level_embed"][l].view(1, 1, -1))
+        shapes = torch.as_tensor([m.shape[-2:] for m in masks], dtype=torch.long, device=self.device)
+        lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+        src = torch.cat(srcs, 1)
+        pos = torch.cat(poses, 1)
+        pad = torch.cat([m.flatten(1) for m in masks], 1)
+        with torch.no_grad():
+            vr = torch.stack([torch.stack([(~m[:, 0, :]).sum(1).float() / m.shape[2],
+                                           (~m[:, :, 0]).sum(1).float() / m.shape[1]], -1) for m in masks], 1)   # [N,L,2]
+            refs = []
+            for l, (h, w) in enumerate(shapes.tolist()):
+                ry, rx = torch.meshgrid(torch.linspace(0.5, h - 0.5, h, device=self.device),
+                                        torch.linspace(0.5, w - 0.5, w, device=self.device), indexing="ij")
+                refs.append(torch.stack((rx.reshape(-1)[None] / (vr[:, None, l, 0] * w),
+                                         ry.reshape(-1)[None] / (vr[:, None, l, 1] * h)), -1))
+            enc_ref = torch.cat(refs, 1)[:, :, None] * vr[:, None]                               # [N,S,L,2]
+        out = src
+        for i in range(self.enc_layers):
+            p = f"{TR}encoder.layers.{i}"
+            a = self._msda(p + ".self_attn", out + pos, enc_ref, out, shapes, lsi, pad)
+            out = self._ln(p + ".norm1", out + self._drop(a))
+            f = self._lin(p + ".linear2", self._drop(F.relu(self._lin(p + ".linear1", out))))
+            out = self._ln(p + ".norm2", out + self._drop(f))
+        memory = out
+
+        qe = self.P[DETR + "query_embed.weight"]
+        C = memory.shape[-1]
+        qpos, tgt = qe[:, :C].unsqueeze(0).expand(N, -1, -1), qe[:, C:].unsqueeze(0).expand(N, -1, -1)
+        ref = self._lin(TR + "reference_points", qpos).sigmoid()
+        init_ref = ref
+        hs, coords, inter = [], [], []
+        o = tgt
+        for lid in range(self.dec_layers):
+            p = f"{TR}decoder.layers.{lid}"
+            ref_in = ref[:, :, None] * (torch.cat([vr, vr], -1) if ref.shape[-1] == 4 else vr)[:, None]
+            q = o + qpos
+            o = self._ln(p + ".norm2", o + self._drop(self._mha(p + ".self_attn", q, o)))
+            a = self._msda(p + ".cross_attn", o + qpos, ref_in, memory, shapes, lsi, pad)
+            o = self._ln(p + ".norm1", o + self._drop(a))
+            f = self._lin(p + ".linear2", self._drop(F.relu(self._lin(p + ".linear1", o))))
+            o = self._ln(p + ".norm3", o + self._drop(f))
+            # box refinement (deformable_transformer.py:363-374); the same expression is the level's predicted box
+            # (segm:154-165), so it is computed once: with grad for the head, detached for the next layer.
+            tmp = self._mlp(f"{DETR}bbox_embed.{lid}", o)
+            rl = inverse_sigmoid(ref)
+            new = (tmp + rl if ref.shape[-1] == 4 else torch.cat([tmp[..., :2] + rl, tmp[..., 2:]], -1)).sigmoid()
+            hs.append(o)
+            coords.append(new)
+            inter.append(ref)                 # the reference this level's head/mask branch uses (init or previous)
+            ref = new.detach()
+        return {"hs": hs, "coords": coords, "level_ref": inter, "last_ref": ref, "memory": memory, "shapes": shapes,
+                "lsi": lsi, "image_size": (H, W), "init_ref": init_ref}
+
+    # ------------------------------------------------------------------ mask branch + dynamic head (segm:324-374, 376-470, 539-575)
+    def _conv(self, p, x):
+        return F.conv2d(x, self.P[p + ".weight"], self.P[p + ".bias"], padding=1)
+
+    def mask_features(self, memory, shapes, lsi):
+        lv = []
+        for l in range(self.L - 1):
+            h, w = shapes[l].tolist()
+            s0 = int(lsi[l])
+            lv.append(memory[:, s0:s0 + h * w].reshape(memory.shape[0], h, w, -1).permute(0, 3, 1, 2))
+        p = "detr.mask_head."
+        x = F.relu(self._conv(p + "lay3", lv[-1]))
+        x = lv[-2] + F.interpolate(x, size=lv[-2].shape[-2:], mode="nearest")
+        x = F.relu(self._conv(p + "lay4", x))
+        x = lv[-3] + F.interpolate(x, size=lv[-3].shape[-2:], mode="nearest")
+        x = F.relu(self._conv(p + "dcn", x))
+        x = F.relu(self._conv(p + "lay1", x))
+        return F.relu(self._conv(p + "lay2", x))                                   # [B, 8, H/8, W/8]
+
+    @staticmethod
+    def _aligned_bilinear(t, factor):
+        if factor == 1:
+            return t
+        h, w = t.shape[2:]
+        t = F.pad(t, pad=(0, 1, 0, 1), mode="replicate")
+        oh, ow = factor * h + 1, factor * w + 1
+        t = F.interpolate(t, size=(oh, ow), mode="bilinear", align_corners=True)
+        t = F.pad(t, pad=(factor // 2, 0, factor // 2, 0), mode="replicate")
+        return t[:, :, :oh - 1, :ow - 1]
+
+    def instance_masks(self, feat, ref_px, params, stride=8, ch=8):
+        """feat [8,h,w] of one image; ref_px [n,2]; params [n,169] -> logits [n, 2h, 2w]."""
+        cin, h, w = feat.shape
+        n = ref_px.shape[0]
+        if n == 0:
+            f = stride // self.mask_stride
+            return (feat.sum() * 0 + params.sum() * 0).expand(0, h * f, w * f)
+        xs = torch.arange(0, w * stride, stride, dtype=torch.float32, device=feat.device) + stride // 2
+        ys = torch.arange(0, h * stride, stride, dtype=torch.float32, device=feat.device) + stride // 2
+        yy, xx = torch.meshgrid(ys, xs, indexing="ij")
+        loc = torch.stack((xx.reshape(-1), yy.reshape(-1)), 0)                     # [2, hw]
+        rel = ref_px[:, :, None] - loc[None]                                       # [n, 2, hw]
+        x = torch.cat([rel, feat.reshape(1, cin, h * w).expand(n, -1, -1)], 1)     # [n, 10, hw]
+        sizes = [(cin + 2) * ch, ch * ch, ch, ch, ch, 1]
+        w0, w1, w2, b0, b1, b2 = torch.split_with_sizes(params, sizes, dim=1)
+        x = F.relu(torch.baddbmm(b0[:, :, None], w0.reshape(n, ch, cin + 2), x))
+        x = F.relu(torch.baddbmm(b1[:, :, None], w1.reshape(n, ch, ch), x))
+        x = torch.baddbmm(b2[:, :, None], w2.reshape(n, 1, ch), x)
+        x = self._aligned_bilinear(x.reshape(n, 1, h, w), stride // self.mask_stride)
+        return x[:, 0]
+
+    # ------------------------------------------------------------------ the training forward
+    def forward(self, frames, det_targets, ref_targets):
+        """-> (loss_dict unweighted, outputs).  frames [2B,3,H,W]; targets as IDOL.prepare_targets builds them."""
+        d = self.dense(frames)
+        key, rf = slice(0, None, 2), slice(1, None, 2)
+        H, W = d["image_size"]
+        scale = torch.tensor([float(W), float(H)], device=self.device)
+        feat = self.mask_features(d["memory"][key], d["shapes"], d["lsi"])
+        levels, indices_list, matched = [], [], None
+        for lvl in range(self.dec_layers):
+            hk = d["hs"][lvl][key]
+            out = {"pred_logits": self._lin(f"{DETR}class_embed.{lvl}", hk), "pred_boxes": d["coords"][lvl][key]}
+            params = self._mlp("detr.controller", hk)
+            indices, matched = self.criterion.matcher(out, det_targets)
+            ref_px = inverse_sigmoid(d["level_ref"][lvl][key]).sigmoid()[..., :2] * scale
+            out["pred_masks"] = [self.instance_masks(feat[b], ref_px[b][sel], params[b][sel])[None, :, None]
+                                 for b, (sel, _) in enumerate(indices)]
+            levels.append(out)
+            indices_list.append(indices)
+        outputs = dict(levels[-1])
+        hs_key, hs_ref = d["hs"][-1][key], d["hs"][-1][rf]
+        ref_cls = self._lin(f"{DETR}class_embed.{self.dec_layers - 1}", hs_ref).sigmoid()
+        outputs["pred_qd"] = crit.select_pos_neg(d["last_ref"][rf], matched, ref_targets, det_targets,
+                                                 self._mlp("detr.reid_embed_head", hs_key),
+                                                 self._mlp("detr.reid_embed_head", hs_ref), ref_cls)
+        outputs["aux_outputs"] = levels[:-1]
+        return self.criterion(outputs, det_targets, ref_targets, indices_list), outputs
+
+    def weighted(self, loss_dict):
+        return {k: v * self.weight_dict[k] for k, v in loss_dict.items() if k in self.weight_dict}
+
+
+class IDOLTrainer:
+    """One optimisation step = zero flat grads, forward, backward, ONE all-reduce of the flat gradient buffer,
+    full-model gradient-norm clipping (train_net.py:110-125, CLIP_VALUE 0.01) and AdamW (train_net.py:132-135:
+    BASE_LR 1e-4, backbone x0.1, WEIGHT_DECAY 1e-4 — configs/ytvis19_r50.yaml:19-30)."""
+
+    def __init__(self, model, base_lr=1e-4, backbone_multiplier=0.1, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8,
+                 clip_value=0.01, process_group=None):
+        self.model, self.flat = model, model.flat
+        self.lrs = (base_lr * backbone_multiplier, base_lr)
+        self.wd, self.betas, self.eps, self.clip = weight_decay, betas, eps, clip_value
+        self.step_count = 0
+        self.pg = process_group
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
+            model.criterion.all_reduce_fn = lambda t: torch.distributed.all_reduce(t, group=process_group)
+        self.scale = torch.ones(1, device=self.flat.w.device)
+
+    def step(self, frames, det_targets, ref_targets):
+        self.flat.g.zero_()
+        loss_dict, _ = self.model(frames, det_targets, ref_targets)
+        weighted = self.model.weighted(loss_dict)
+        total = sum(weighted.values())
+        total.backward()
+        return self.apply_gradients(), total.detach(), weighted
+
+    def apply_gradients(self):
+        g = self.flat.g
+        if self.world > 1:
+            torch.distributed.all_reduce(g, group=self.pg)                       # sum; the 1/world is folded below
+        norm = torch.linalg.vector_norm(g) / self.world
+        if self.clip and self.clip > 0:
+            self.scale = (self.clip / (norm + 1e-6)).clamp(max=1.0).reshape(1) / self.world   # clip_grad_norm_
+        else:
+            self.scale = torch.full((1,), 1.0 / self.world, device=g.device)
+        self.step_count += 1
+        f = self.flat
+        for (lo, hi), lr in zip(f.groups(), self.lrs):
+            adamw_(f.w[lo:hi], g[lo:hi], f.m[lo:hi], f.v[lo:hi], lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                   self.step_count, self.scale)
+        return norm

@@ -89,6 +89,45 @@ def synthetic_clip(num_frames, height, width, seed=0):
     return [torch.randint(0, 256, (3, height, width), generator=g).float() for _ in range(num_frames)]
 
 
+def synthetic_targets(num_videos, height, width, seed=0, insts=3, num_classes=40):
+    """Ground truth of `num_videos` (key, ref) frame pairs in the format IDOL.prepare_targets produces
+    (projects/IDOL/idol/idol.py:296-324): per frame {"labels","boxes" (cx,cy,w,h normalised),"masks" [n,H,W] bool,
+    "inst_id","valid"}.  Instances are axis-aligned rectangles that drift between key and ref; in every odd video the
+    last instance has left the reference frame (inst_id -1, valid False, empty box and mask), the case
+    pos_neg_select.py:28-36 handles.  -> (det_targets, ref_targets)"""
+    g = _gen("targets", seed)
+    det, ref = [], []
+    for v in range(num_videos):
+        labels = torch.randint(0, num_classes, (insts,), generator=g)
+        cx = (torch.rand(insts, generator=g) * 0.6 + 0.2)
+        cy = (torch.rand(insts, generator=g) * 0.6 + 0.2)
+        bw = (torch.rand(insts, generator=g) * 0.25 + 0.1)
+        bh = (torch.rand(insts, generator=g) * 0.25 + 0.1)
+        shift = (torch.rand(insts, 2, generator=g) - 0.5) * 0.1
+        frames = []
+        for f in range(2):
+            x0 = ((cx + f * shift[:, 0] - bw / 2).clamp(0, 1) * width).round()
+            x1 = ((cx + f * shift[:, 0] + bw / 2).clamp(0, 1) * width).round()
+            y0 = ((cy + f * shift[:, 1] - bh / 2).clamp(0, 1) * height).round()
+            y1 = ((cy + f * shift[:, 1] + bh / 2).clamp(0, 1) * height).round()
+            ids = torch.arange(insts) + 10 * v
+            valid = torch.ones(insts, dtype=torch.bool)
+            if f == 1 and v % 2 == 1:
+                x0[-1] = x1[-1] = y0[-1] = y1[-1] = 0
+                ids[-1] = -1
+                valid[-1] = False
+            ys = torch.arange(height).view(1, height, 1)
+            xs = torch.arange(width).view(1, 1, width)
+            masks = (xs >= x0.view(-1, 1, 1)) & (xs < x1.view(-1, 1, 1)) & (ys >= y0.view(-1, 1, 1)) & \
+                    (ys < y1.view(-1, 1, 1))
+            boxes = torch.stack([(x0 + x1) / 2 / width, (y0 + y1) / 2 / height, (x1 - x0) / width,
+                                 (y1 - y0) / height], -1)
+            frames.append({"labels": labels.clone(), "boxes": boxes, "masks": masks, "inst_id": ids, "valid": valid})
+        det.append(frames[0])
+        ref.append(frames[1])
+    return det, ref
+
+
 def make_msda_inputs(N, Lq, M, D, shapes, P, seed, dtype=torch.float32, loc_range=(0.0, 1.0)):
     """MSDA input recipe of the reference test (projects/IDOL/idol/models/ops/test.py:33-36):
     value ~ U(0, .01), sampling locations ~ U(loc_range), attention weights normalised over (L, P)."""
