@@ -1,0 +1,102 @@
+"""IDOL training step on the B200: the dense forward/backward with the sm_100a MSDA forward + backward kernels against
+the REFERENCE's own losses and gradients (tests/golden/make_idol_train_golden.py), the flat-buffer AdamW kernel against
+torch.optim.AdamW, and the trainer step against clip_grad_norm_ + AdamW built the way train_net.py:94-140 builds them."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from test_idol_train_host import B, GOLD, H, SEED, W, compare_with_golden
+from vnext_b200 import _cabi
+from vnext_b200.idol import train as T
+from vnext_b200.idol.state_spec import idol_r50_state_spec
+from vnext_b200.synth import fill_state_dict, synthetic_clip, synthetic_targets
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+
+def _cuda_targets(seed=SEED, b=B, h=H, w=W):
+    det, ref = synthetic_targets(b, h, w, seed)
+    mv = lambda ts: [{k: v.cuda() for k, v in t.items()} for t in ts]
+    return mv(det), mv(ref)
+
+
+@pytest.fixture()
+def strict_fp32():
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_train_step_matches_reference(strict_fp32):
+    gold = dict(np.load(GOLD))
+    sd = fill_state_dict(idol_r50_state_spec(), SEED)
+    model = T.IDOLTrainModel(sd, device="cuda", dropout=0.0).train()
+    frames = torch.stack(synthetic_clip(2 * B, H, W, SEED)).cuda()
+    det, ref = _cuda_targets()
+    n0 = _cabi.lib().vnext_launch_count()
+    random.seed(0)
+    loss_dict, outputs = model(frames, det, ref)
+    total = sum(model.weighted(loss_dict).values())
+    total.backward()
+    torch.cuda.synchronize()
+    assert _cabi.lib().vnext_launch_count() - n0 >= 24          # 12 MSDA forwards + 12 backwards, own kernels
+    for b in range(B):                                          # simOTA picked as many queries as in the reference
+        assert outputs["pred_masks"][b].shape[1] == int(gold[f"lvl5_b{b}_selected"].sum())
+    np.testing.assert_allclose(float(total), float(gold["total"]), rtol=2e-3)
+    worst = compare_with_golden(model, gold, loss_dict, rtol_loss=2e-3, rtol_norm=1e-2, tol_grad=1e-2)
+    print("worst grad-norm rel err vs reference:", worst)
+
+
+def test_adamw_kernel_matches_torch():
+    g = torch.Generator().manual_seed(0)
+    n = 4096 * 37
+    w0 = torch.randn(n, generator=g).cuda()
+    p = torch.nn.Parameter(w0.clone())
+    opt = torch.optim.AdamW([p], lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    w, m, v = w0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    scale = torch.full((1,), 0.5, device="cuda")
+    for step in range(1, 6):
+        grad = torch.randn(n, generator=g).cuda()
+        p.grad = grad * 0.5
+        opt.step()
+        T.adamw_(w, grad, m, v, 3e-3, 0.9, 0.999, 1e-8, 1e-2, step, scale)
+        assert (w - p.detach()).abs().max().item() < 2e-6, step
+    with pytest.raises(RuntimeError, match="multiple of 4"):
+        T.adamw_(w[:6], grad[:6], m[:6], v[:6], 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, scale)
+
+
+def test_trainer_step_equals_clip_plus_adamw(strict_fp32):
+    sd = fill_state_dict(idol_r50_state_spec(), 5)
+    model = T.IDOLTrainModel(sd, device="cuda", dropout=0.0).train()
+    trainer = T.IDOLTrainer(model)
+    frames = torch.stack(synthetic_clip(2 * B, H, W, 5)).cuda()
+    det, ref = _cuda_targets(seed=5)
+    w_before = model.flat.w.clone()
+    # what train_net.py would do with these gradients: per-parameter AdamW groups + full-model clipping at 0.01
+    random.seed(1)
+    model.flat.g.zero_()
+    loss_dict, _ = model(frames, det, ref)
+    sum(model.weighted(loss_dict).values()).backward()
+    clones = {k: torch.nn.Parameter(p.detach().clone()) for k, p in model.flat.params.items()}
+    for k, c in clones.items():
+        c.grad = model.flat.params[k].grad.clone()
+    opt = torch.optim.AdamW([{"params": [c], "lr": 1e-4 * (0.1 if "backbone" in k else 1.0), "weight_decay": 1e-4}
+                             for k, c in clones.items()], 1e-4)
+    want_norm = torch.nn.utils.clip_grad_norm_(list(clones.values()), 0.01)
+    opt.step()
+    norm = trainer.apply_gradients()
+    torch.cuda.synchronize()
+    assert abs(float(norm) - float(want_norm)) / float(want_norm) < 1e-4
+    assert not torch.equal(w_before, model.flat.w)
+    worst = max((model.flat.params[k].detach() - c.detach()).abs().max().item() for k, c in clones.items())
+    assert worst < 1e-6, worst
+    # and full steps run back to back: finite losses, parameters keep moving
+    random.seed(2)
+    for _ in range(2):
+        _, total, _ = trainer.step(frames, det, ref)
+        assert torch.isfinite(total)
+    assert trainer.step_count == 3

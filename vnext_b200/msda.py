@@ -130,11 +130,16 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     if value.dtype == torch.bfloat16:
         ws = torch.empty(value.shape, dtype=torch.float32, device=value.device)
         ws_ptr = ws.data_ptr()
+    e = value.element_size()
+    info = {"bytes": float(N) * (e * (2 * S * M * D + Lq * M * D) + loc_in.element_size() * 6 * Lq * M * L * P),
+            "N": N, "Lq": Lq, "S": S}                  # SURVEY §8d bwd_bytes
     with torch.cuda.device(value.device):
-        rc = _cabi.lib().vnext_msda_backward(
-            _DTYPES[value.dtype], value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
-            loc_in.data_ptr(), attn_in.data_ptr(), grad_output.data_ptr(), N, S, M, D, L, Lq, P,
-            grad_value.data_ptr(), grad_loc.data_ptr(), grad_attn.data_ptr(), ws_ptr, _stream(value))
+        rc = _cabi.timed_call(
+            "msda_bwd_enc" if Lq == S else "msda_bwd_dec", info, value,
+            lambda: _cabi.lib().vnext_msda_backward(
+                _DTYPES[value.dtype], value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                loc_in.data_ptr(), attn_in.data_ptr(), grad_output.data_ptr(), N, S, M, D, L, Lq, P,
+                grad_value.data_ptr(), grad_loc.data_ptr(), grad_attn.data_ptr(), ws_ptr, _stream(value)))
     _cabi.check(rc, "ms_deform_attn_backward")
     if grad_loc.dtype != sampling_loc.dtype:
         grad_loc = grad_loc.to(sampling_loc.dtype)
