@@ -100,3 +100,28 @@ def test_trainer_step_equals_clip_plus_adamw(strict_fp32):
         _, total, _ = trainer.step(frames, det, ref)
         assert torch.isfinite(total)
     assert trainer.step_count == 3
+
+
+def test_idol_facade_training_forward(strict_fp32):
+    """`IDOL.forward(batched_inputs)` in training mode returns the reference's weighted loss dict (idol.py:205-215)."""
+    from test_idol_train_host import fake_batched_inputs
+    from vnext_b200.idol.meta_arch import IDOL
+    gold = dict(np.load(GOLD))
+    batched, _, _ = fake_batched_inputs()
+    m = IDOL(state_dict=fill_state_dict(idol_r50_state_spec(), SEED), device="cuda", precision="fp32")
+    m.dropout = 0.0
+    m.train()
+    random.seed(0)
+    losses = m(batched)
+    assert len(losses) == 7 * 6
+    np.testing.assert_allclose(float(sum(losses.values())), float(gold["total"]), rtol=2e-3)
+    np.testing.assert_allclose(float(losses["loss_reid"]), 2.0 * float(gold["loss/loss_reid"]), rtol=2e-3)
+    # ragged frame sizes are padded like ImageList.from_tensors: runs, finite
+    batched[1]["image"] = [f[:, :80, :112] for f in batched[1]["image"]]
+    for inst in batched[1]["instances"]:
+        inst.image_size = (80, 112)
+        inst.gt_masks.tensor = inst.gt_masks.tensor[:, :80, :112]
+    random.seed(0)
+    assert torch.isfinite(sum(m(batched).values()))
+    m.sync_engine()                                   # trained weights -> inference engine
+    assert m.engine is not None

@@ -87,3 +87,43 @@ def test_adamw_refuses_cpu():
     z = torch.zeros(4)
     with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
         T.adamw_(z, z, z, z, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, torch.ones(1))
+
+
+class _Boxes:
+    def __init__(self, t):
+        self.tensor = t
+
+
+class FakeInstances:
+    """Duck type of detectron2.structures.Instances as the YTVIS dataset mapper fills it."""
+
+    def __init__(self, t, h, w):
+        from vnext_b200.idol.criterion import cxcywh_to_xyxy
+        self.image_size = (h, w)
+        self.gt_classes = t["labels"]
+        self.gt_boxes = _Boxes(cxcywh_to_xyxy(t["boxes"]) * torch.tensor([w, h, w, h], dtype=torch.float))
+        self.gt_masks = _Boxes(t["masks"])
+        self.gt_ids = t["inst_id"]
+
+
+def fake_batched_inputs(seed=SEED):
+    frames = synthetic_clip(2 * B, H, W, seed)
+    det, ref = synthetic_targets(B, H, W, seed)
+    return [{"image": [frames[2 * v], frames[2 * v + 1]],
+             "instances": [FakeInstances(det[v], H, W), FakeInstances(ref[v], H, W)]} for v in range(B)], det, ref
+
+
+def test_prepare_targets_matches_reference_format():
+    from vnext_b200.idol.meta_arch import IDOL
+    batched, det, ref = fake_batched_inputs()
+    m = IDOL(device="cpu")
+    d2, r2 = m.prepare_targets([i for v in batched for i in v["instances"]])
+    for a, b in zip(det + ref, d2 + r2):
+        assert torch.equal(a["labels"], b["labels"]) and torch.equal(a["valid"], b["valid"])
+        assert torch.allclose(a["boxes"], b["boxes"], atol=1e-6) and torch.equal(a["masks"], b["masks"])
+    # an object missing from the KEY frame is dropped from both frames (idol.py:313-321)
+    insts = [i for v in batched for i in v["instances"]]
+    insts[0].gt_ids = insts[0].gt_ids.clone()
+    insts[0].gt_ids[1] = -1
+    d3, r3 = m.prepare_targets(insts)
+    assert len(d3[0]["labels"]) == len(r3[0]["labels"]) == 2 and len(d3[1]["labels"]) == 3

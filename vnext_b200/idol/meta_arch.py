@@ -1,9 +1,11 @@
 """`IDOL` META_ARCH facade (projects/IDOL/idol/idol.py:71-295): same cfg keys and `batched_inputs`; the dense
 per-frame path runs on the B200 engine in chunks of BATCH_INFER_LEN frames (idol.py:252-274).  The online tracker
 (`IDOL_Tracker`, idol.py:275-295 / models/tracker.py) is host-side association and is NOT part of this round's path
-(SURVEY §8f): `forward` hands the dense outputs to `self.tracker_fn(output, (height, width), image_size)` when one is
+(SURVEY §8f): in eval mode `forward` hands the dense outputs to `self.tracker_fn(output, (height, width), image_size)` when one is
 attached (e.g. the reference's own `IDOL.inference` bound to its tracker) and raises otherwise; `dense_forward`
-returns exactly what the reference's `detr.inference_forward` returns."""
+returns exactly what the reference's `detr.inference_forward` returns.  In training mode `forward` returns the weighted
+loss dict of idol.py:205-215 from the differentiable dense path (vnext_b200/idol/train.py: MSDA forward/backward
+kernels under autograd) and the host-side criterion (criterion.py)."""
 import torch
 from torch import nn
 
@@ -25,11 +27,22 @@ class IDOL(nn.Module):
         self.device_name = g("MODEL.DEVICE", device)
         self.precision = precision
         self.tracker_fn = tracker_fn
+        self.dropout = g("MODEL.IDOL.DROPOUT", 0.1)
+        from .criterion import default_weight_dict
+        self.weight_dict = default_weight_dict(g("MODEL.IDOL.CLASS_WEIGHT", 2.0), g("MODEL.IDOL.L1_WEIGHT", 5.0),
+                                               g("MODEL.IDOL.GIOU_WEIGHT", 2.0), g("MODEL.IDOL.REID_WEIGHT", 2.0),
+                                               g("MODEL.IDOL.MASK_WEIGHT", 2.0), g("MODEL.IDOL.DICE_WEIGHT", 5.0),
+                                               g("MODEL.IDOL.DEC_LAYERS", 6), g("MODEL.IDOL.DEEP_SUPERVISION", True))
         self.engine = None
+        self._state_dict = None
+        self._train_model = None
         if state_dict is not None:
             self.load_reference_state_dict(state_dict)
 
-    def load_reference_state_dict(self, state_dict):
+    def load_reference_state_dict(self, state_dict, keep_train_model=False):
+        self._state_dict = state_dict
+        if not keep_train_model:
+            self._train_model = None
         spec = idol_r50_state_spec(self.num_queries, self.num_classes)
         missing = [k for k in spec if k not in state_dict]
         if missing:
@@ -52,9 +65,54 @@ class IDOL(nn.Module):
             outs.append({k: o[k] for k in ("pred_logits", "pred_boxes", "pred_inst_embed", "pred_masks")})
         return {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}
 
+    # ------------------------------------------------------------------ training (idol.py:205-215, :296-324)
+    def train_model(self):
+        """The differentiable dense path (vnext_b200/idol/train.py), created on first use from the loaded weights."""
+        if self._train_model is None:
+            if self._state_dict is None:
+                raise RuntimeError("no weights loaded: call load_reference_state_dict(checkpoint['model'])")
+            from .train import IDOLTrainModel
+            self._train_model = IDOLTrainModel(self._state_dict, device=self.device_name, num_classes=self.num_classes,
+                                               num_queries=self.num_queries, dropout=self.dropout,
+                                               pixel_mean=self.pixel_mean, pixel_std=self.pixel_std,
+                                               mask_stride=self.mask_stride, weight_dict=self.weight_dict)
+        return self._train_model
+
+    def sync_engine(self):
+        """Rebuild the inference engine from the trained weights (call before evaluating after training steps)."""
+        self.load_reference_state_dict(self.train_model().reference_state_dict(), keep_train_model=True)
+
+    def prepare_targets(self, targets):
+        """Per-frame `Instances`-like objects (gt_classes, gt_boxes.tensor xyxy pixels, gt_masks.tensor, gt_ids,
+        image_size) in key, ref, key, ref order -> (det_targets, ref_targets), objects absent from the key frame
+        dropped from both (idol.py:296-324)."""
+        from .criterion import xyxy_to_cxcywh
+        dev = self.device_name
+        new = []
+        for t in targets:
+            h, w = t.image_size
+            boxes = t.gt_boxes.tensor.to(dev) / torch.as_tensor([w, h, w, h], dtype=torch.float, device=dev)
+            ids = t.gt_ids.to(dev)
+            new.append({"labels": t.gt_classes.to(dev), "boxes": xyxy_to_cxcywh(boxes),
+                        "masks": t.gt_masks.tensor.to(dev), "inst_id": ids, "valid": ids != -1})
+        det, ref = new[0::2], new[1::2]
+        for d, r in zip(det, ref):
+            if not bool(d["valid"].all()):
+                keep = d["valid"].clone()
+                for k in list(d):
+                    d[k] = d[k][keep]
+                for k in list(r):
+                    r[k] = r[k][keep]
+        return det, ref
+
     def forward(self, batched_inputs):
         if self.training:
-            raise NotImplementedError("vnext_b200 IDOL: the training step is not on this round's hot path")
+            frames = [f for video in batched_inputs for f in video["image"]]
+            gt = [inst for video in batched_inputs for inst in video["instances"]]
+            det, ref = self.prepare_targets(gt)
+            model = self.train_model().train()
+            loss_dict, _ = model(frames, det, ref)
+            return model.weighted(loss_dict)
         output = self.dense_forward(batched_inputs)
         if self.tracker_fn is None:
             raise NotImplementedError("IDOL's online tracker (models/tracker.py) is host-side post-processing outside "

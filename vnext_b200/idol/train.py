@@ -230,14 +230,21 @@ class IDOLTrainModel(nn.Module):
 
     # ------------------------------------------------------------------ dense forward over all frames
     def dense(self, frames):
-        """frames [N,3,H,W] float 0..255 (N = 2 x videos: key, ref, key, ref ...), all of one size.
-        -> dict(hs [dec,N,nq,C], memory [N,S,C], init_ref [N,nq,2], inter_ref [dec,N,nq,4], shapes, lsi, image_size)"""
-        N, _, H, W = frames.shape
-        Hp, Wp = (H + 31) // 32 * 32, (W + 31) // 32 * 32
-        x = (frames.to(self.device, torch.float32) - self.mean) / self.std
-        x = F.pad(x, (0, Wp - W, 0, Hp - H))
+        """frames: [N,3,H,W] tensor or list of N [3,h_i,w_i] tensors, float/uint8 0..255 (N = 2 x videos: key, ref,
+        key, ref ...); ragged sizes are zero-padded after normalisation like ImageList.from_tensors(…, 32)
+        (idol.py:487-497).  -> dict(hs, coords, level_ref, last_ref, memory [N,S,C], shapes, lsi, sizes [(h,w)]*N)"""
+        if torch.is_tensor(frames):
+            frames = list(frames)
+        N = len(frames)
+        sizes = [tuple(f.shape[-2:]) for f in frames]
+        Hp = (max(h for h, _ in sizes) + 31) // 32 * 32
+        Wp = (max(w for _, w in sizes) + 31) // 32 * 32
+        x = torch.zeros(N, 3, Hp, Wp, device=self.device)
         mask = torch.ones(N, Hp, Wp, dtype=torch.bool, device=self.device)
-        mask[:, :H, :W] = False
+        for i, f in enumerate(frames):
+            h, w = sizes[i]
+            x[i, :, :h, :w] = (f.to(self.device, torch.float32) - self.mean[0]) / self.std[0]
+            mask[i, :h, :w] = False
         feats = self.backbone(x)
         srcs, masks, poses = [], [], []
         for l, name in enumerate(("res3", "res4", "res5", "res5")):
@@ -302,7 +309,7 @@ class IDOLTrainModel(nn.Module):
             inter.append(ref)                 # the reference this level's head/mask branch uses (init or previous)
             ref = new.detach()
         return {"hs": hs, "coords": coords, "level_ref": inter, "last_ref": ref, "memory": memory, "shapes": shapes,
-                "lsi": lsi, "image_size": (H, W), "init_ref": init_ref}
+                "lsi": lsi, "sizes": sizes, "init_ref": init_ref}
 
     # ------------------------------------------------------------------ mask branch + dynamic head (segm:324-374, 376-470, 539-575)
     def _conv(self, p, x):
@@ -357,11 +364,11 @@ class IDOLTrainModel(nn.Module):
 
     # ------------------------------------------------------------------ the training forward
     def forward(self, frames, det_targets, ref_targets):
-        """-> (loss_dict unweighted, outputs).  frames [2B,3,H,W]; targets as IDOL.prepare_targets builds them."""
+        """-> (loss_dict unweighted, outputs).  frames [2B,3,H,W] or a list of 2B [3,h,w]; targets as
+        IDOL.prepare_targets builds them."""
         d = self.dense(frames)
         key, rf = slice(0, None, 2), slice(1, None, 2)
-        H, W = d["image_size"]
-        scale = torch.tensor([float(W), float(H)], device=self.device)
+        scale = torch.tensor([[float(w), float(h)] for h, w in d["sizes"][key]], device=self.device)[:, None]  # segm:177-181
         feat = self.mask_features(d["memory"][key], d["shapes"], d["lsi"])
         levels, indices_list, matched = [], [], None
         for lvl in range(self.dec_layers):
@@ -413,7 +420,9 @@ class IDOLTrainer:
         total.backward()
         return self.apply_gradients(), total.detach(), weighted
 
-    def apply_gradients(self):
+    def reduce_gradients(self):
+        """Sum the flat gradient buffer over ranks (one collective) and set the device-side scale that turns it into
+        the clipped mean gradient.  -> L2 norm of the mean gradient (a device scalar; nothing is synchronised)."""
         g = self.flat.g
         if self.world > 1:
             torch.distributed.all_reduce(g, group=self.pg)                       # sum; the 1/world is folded below
@@ -422,9 +431,13 @@ class IDOLTrainer:
             self.scale = (self.clip / (norm + 1e-6)).clamp(max=1.0).reshape(1) / self.world   # clip_grad_norm_
         else:
             self.scale = torch.full((1,), 1.0 / self.world, device=g.device)
+        return norm
+
+    def apply_gradients(self):
+        norm = self.reduce_gradients()
         self.step_count += 1
         f = self.flat
         for (lo, hi), lr in zip(f.groups(), self.lrs):
-            adamw_(f.w[lo:hi], g[lo:hi], f.m[lo:hi], f.v[lo:hi], lr, self.betas[0], self.betas[1], self.eps, self.wd,
+            adamw_(f.w[lo:hi], f.g[lo:hi], f.m[lo:hi], f.v[lo:hi], lr, self.betas[0], self.betas[1], self.eps, self.wd,
                    self.step_count, self.scale)
         return norm
