@@ -351,7 +351,8 @@ def train_arm(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     NF, H, W = WORKLOADS["idol_train"]
-    model = T.IDOLTrainModel(fill_state_dict(idol_r50_state_spec(), 0), device=dev, dropout=0.1).train()
+    model = T.IDOLTrainModel(fill_state_dict(idol_r50_state_spec(), 0), device=dev, dropout=0.1,
+                             precision=args.precision).train()
     trainer = T.IDOLTrainer(model)
     host = torch.stack(synthetic_clip(NF, H, W, rank)).to(torch.uint8).pin_memory()
     det, ref = synthetic_targets(NF // 2, H, W, rank)
@@ -415,7 +416,7 @@ def train_arm(args, rank, world, local_rank):
         print(json.dumps({
             "metric": TRAIN_METRIC, "value": round(fps, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (cuDNN/cuBLAS default TF32 convs), MSDA fwd/bwd fp32",
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32 GEMMs/convs, f32 MSDA + accumulate" if args.precision == "tf32" else "f32 (cuDNN default TF32 convs)",
             "data": "synthetic",
             "config": {"workload": f"IDOL-R50 training step, {NF // 2} videos x (key, ref) frames {H}x{W} per GPU, 300 "
                                    "queries, dropout 0.1, simOTA + 7 loss terms x 6 levels, AdamW lr 1e-4 (backbone x0.1), "

@@ -25,6 +25,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .. import _cabi
+from ..linear import linear as tc_linear
 from ..msda import MSDeformAttnFunction
 from . import criterion as crit
 from .state_spec import idol_r50_state_spec
@@ -96,11 +97,52 @@ def adamw_(w, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale):
     _cabi.check(rc, "vnext_adamw")
 
 
+class TcLinear(torch.autograd.Function):
+    """y = relu?(x W^T + b) with the forward GEMM and the data-gradient GEMM (dX = dY W) on this repo's tcgen05 TF32
+    kernel (csrc/gemm_tcgen05.cu, bias / ReLU fused in the epilogue); the weight gradient dW = dY^T X contracts over the
+    row dimension, which that kernel would need both operands transposed for, and stays on cuBLAS this round."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        x2 = x.reshape(-1, x.shape[-1])
+        x2 = x2 if x2.is_contiguous() else x2.contiguous()
+        out = tc_linear(x2, weight.contiguous(), bias, relu=relu)
+        ctx.relu = relu
+        ctx.save_for_backward(x2, weight, out if relu else None)
+        ctx.has_bias = bias is not None
+        return out.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, grad):
+        x2, weight, out = ctx.saved_tensors
+        g = grad.reshape(-1, grad.shape[-1])
+        if ctx.relu:
+            g = g * (out > 0)
+        g = g if g.is_contiguous() else g.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            if weight.shape[0] % 4 == 0:
+                gx = tc_linear(g, weight.t().contiguous())
+            else:
+                gx = g @ weight
+            gx = gx.view(*grad.shape[:-1], weight.shape[1])
+        if ctx.needs_input_grad[1]:
+            gw = g.t() @ x2
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g.sum(0)
+        return gx, gw, gb, None
+
+
 class IDOLTrainModel(nn.Module):
     def __init__(self, state_dict, device="cuda", num_classes=40, num_queries=300, dropout=0.1, freeze_at=2,
                  pixel_mean=(123.675, 116.280, 103.530), pixel_std=(58.395, 57.120, 57.375), mask_stride=4,
-                 weight_dict=None, heads=8, levels=4, points=4):
+                 weight_dict=None, heads=8, levels=4, points=4, precision="fp32"):
         super().__init__()
+        if precision not in ("fp32", "tf32"):
+            raise ValueError("precision must be 'fp32' (cuBLAS fp32 linears, strict parity) or 'tf32' (tcgen05 linears)")
+        self.tc = precision == "tf32"
+        if self.tc:                                   # weight-gradient GEMMs (cuBLAS) in TF32 as well; process-global flag
+            torch.backends.cuda.matmul.allow_tf32 = True
         self.device = torch.device(device)
         spec = idol_r50_state_spec(num_queries, num_classes)
         missing = [k for k in spec if k not in state_dict]
@@ -140,17 +182,21 @@ class IDOLTrainModel(nn.Module):
     def _drop(self, x):
         return F.dropout(x, self.dropout, self.training) if self.dropout > 0 else x
 
-    def _lin(self, p, x):
-        return F.linear(x, self.P[p + ".weight"], self.P[p + ".bias"])
+    def _linear(self, x, w, b, relu=False):
+        if self.tc:
+            return TcLinear.apply(x, w, b, relu)
+        y = F.linear(x, w, b)
+        return F.relu(y) if relu else y
+
+    def _lin(self, p, x, relu=False):
+        return self._linear(x, self.P[p + ".weight"], self.P[p + ".bias"], relu)
 
     def _ln(self, p, x):
         return F.layer_norm(x, (x.shape[-1],), self.P[p + ".weight"], self.P[p + ".bias"], 1e-5)
 
     def _mlp(self, p, x, n=3):
         for i in range(n):
-            x = self._lin(f"{p}.layers.{i}", x)
-            if i < n - 1:
-                x = F.relu(x)
+            x = self._lin(f"{p}.layers.{i}", x, relu=i < n - 1)
         return x
 
     def _conv_bn(self, p, x, stride=1, padding=0, relu=True):
@@ -203,7 +249,7 @@ class IDOLTrainModel(nn.Module):
         n_off = M * L * K * 2
         w = torch.cat([self.P[p + ".sampling_offsets.weight"], self.P[p + ".attention_weights.weight"]], 0)
         b = torch.cat([self.P[p + ".sampling_offsets.bias"], self.P[p + ".attention_weights.bias"]], 0)
-        oa = F.linear(query, w, b)                                              # one pass over the queries for both
+        oa = self._linear(query, w, b)                                          # one pass over the queries for both
         off = oa[..., :n_off].reshape(N, Lq, M, L, K, 2)
         aw = torch.softmax(oa[..., n_off:].reshape(N, Lq, M, L * K), -1).view(N, Lq, M, L, K)
         if ref.shape[-1] == 2:
@@ -218,15 +264,15 @@ class IDOLTrainModel(nn.Module):
         """nn.MultiheadAttention(q=k=q_in, v=v_in) of the decoder self-attention (deformable_transformer.py:306-313)."""
         C = q_in.shape[-1]
         w, b = self.P[p + ".in_proj_weight"], self.P[p + ".in_proj_bias"]
-        qk = F.linear(q_in, w[:2 * C], b[:2 * C])
-        v = F.linear(v_in, w[2 * C:], b[2 * C:])
+        qk = self._linear(q_in, w[:2 * C], b[:2 * C])
+        v = self._linear(v_in, w[2 * C:], b[2 * C:])
         B, Lq, _ = qk.shape
         d = C // self.M
         q = qk[..., :C].reshape(B, Lq, self.M, d).transpose(1, 2)
         k = qk[..., C:].reshape(B, Lq, self.M, d).transpose(1, 2)
         v = v.reshape(B, Lq, self.M, d).transpose(1, 2)
         o = F.scaled_dot_product_attention(q, k, v, dropout_p=self.dropout if self.training else 0.0)
-        return F.linear(o.transpose(1, 2).reshape(B, Lq, C), self.P[p + ".out_proj.weight"], self.P[p + ".out_proj.bias"])
+        return self._linear(o.transpose(1, 2).reshape(B, Lq, C), self.P[p + ".out_proj.weight"], self.P[p + ".out_proj.bias"])
 
     # ------------------------------------------------------------------ dense forward over all frames
     def dense(self, frames):
@@ -279,7 +325,7 @@ class IDOLTrainModel(nn.Module):
             p = f"{TR}encoder.layers.{i}"
             a = self._msda(p + ".self_attn", out + pos, enc_ref, out, shapes, lsi, pad)
             out = self._ln(p + ".norm1", out + self._drop(a))
-            f = self._lin(p + ".linear2", self._drop(F.relu(self._lin(p + ".linear1", out))))
+            f = self._lin(p + ".linear2", self._drop(self._lin(p + ".linear1", out, relu=True)))
             out = self._ln(p + ".norm2", out + self._drop(f))
         memory = out
 
@@ -297,7 +343,7 @@ class IDOLTrainModel(nn.Module):
             o = self._ln(p + ".norm2", o + self._drop(self._mha(p + ".self_attn", q, o)))
             a = self._msda(p + ".cross_attn", o + qpos, ref_in, memory, shapes, lsi, pad)
             o = self._ln(p + ".norm1", o + self._drop(a))
-            f = self._lin(p + ".linear2", self._drop(F.relu(self._lin(p + ".linear1", o))))
+            f = self._lin(p + ".linear2", self._drop(self._lin(p + ".linear1", o, relu=True)))
             o = self._ln(p + ".norm3", o + self._drop(f))
             # box refinement (deformable_transformer.py:363-374); the same expression is the level's predicted box
             # (segm:154-165), so it is computed once: with grad for the head, detached for the next layer.
