@@ -50,26 +50,61 @@ def compare_with_golden(model, gold, loss_dict, rtol_loss, rtol_norm, tol_grad):
     return worst
 
 
+def check_assignment(gold, outputs, batched):
+    """simOTA picked exactly the reference's queries / ground truths at every decoder level."""
+    for lvl in range(6):
+        for b in range(B):
+            want_sel, want_gt = gold[f"lvl{lvl}_b{b}_selected"], gold[f"lvl{lvl}_b{b}_gt"]
+            if batched:
+                a = outputs["assign"]
+                sel = a["sel"][lvl, b].cpu().numpy()
+                assert np.array_equal(sel, want_sel)
+                assert np.array_equal(a["gt_of"][lvl, b].cpu().numpy()[sel], want_gt)
+                assert np.array_equal(a["best_q"][lvl, b].cpu().numpy()[:len(gold[f"lvl{lvl}_b{b}_matched"])],
+                                      gold[f"lvl{lvl}_b{b}_matched"])
+            elif lvl == 5:
+                assert outputs["pred_masks"][b].shape[1] == int(want_sel.sum())
+
+
 @pytest.mark.timeout(900)
-def test_train_forward_backward_matches_reference(monkeypatch):
+@pytest.mark.parametrize("batched", [False, True])
+def test_train_forward_backward_matches_reference(monkeypatch, batched):
     gold = dict(np.load(GOLD))
     monkeypatch.setattr(T, "MSDeformAttnFunction", OracleMSDA)
     sd = fill_state_dict(idol_r50_state_spec(), SEED)
-    model = T.IDOLTrainModel(sd, device="cpu", dropout=0.0).train()
+    model = T.IDOLTrainModel(sd, device="cpu", dropout=0.0, batched=batched).train()
     assert len(model.flat.params) == 360 and all(p.grad.data_ptr() >= model.flat.g.data_ptr() for p in model.parameters())
     frames = torch.stack(synthetic_clip(2 * B, H, W, SEED))
     det, ref = synthetic_targets(B, H, W, SEED)
     random.seed(0)
     loss_dict, outputs = model(frames, det, ref)
     assert set(loss_dict) == {k[5:] for k in gold if k.startswith("loss/")}
+    check_assignment(gold, outputs, batched)
     total = sum(model.weighted(loss_dict).values())
-    np.testing.assert_allclose(float(total), float(gold["total"]), rtol=1e-4)
+    np.testing.assert_allclose(float(total.detach()), float(gold["total"]), rtol=1e-4)
     total.backward()
     worst = compare_with_golden(model, gold, loss_dict, rtol_loss=1e-4, rtol_norm=2e-3, tol_grad=2e-3)
     print("worst grad-norm rel err", worst)
     # gradients landed in the flat buffer (views), frozen tensors got none
     assert float(model.flat.g.abs().sum()) > 0
     assert all(not v.requires_grad for v in model.frozen.values())
+
+
+def test_batched_matcher_repair_loop_falls_back_to_sequential():
+    """A ground truth no query wants (the reference's `while` loop, matcher.py:151-162) goes through the sequential code:
+    two identical GT boxes compete for the same single best query."""
+    from vnext_b200.idol import criterion as seq
+    from vnext_b200.idol import criterion_batched as cb
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(1, 40, 5, generator=g) - 3
+    boxes = torch.rand(1, 40, 4, generator=g) * 0.2 + 0.4
+    boxes[0, :, 2:] = 0.02                                                   # tiny boxes: IoU ~ 0 -> dynamic k = 1
+    tgt = [{"labels": torch.tensor([1, 1]), "boxes": torch.tensor([[0.5, 0.5, 0.3, 0.3], [0.5, 0.5, 0.3, 0.3]])}]
+    ind, mq = seq.simota_match(logits.clone(), boxes.clone(), tgt)
+    gtb, gtl, ex = cb.pad_targets(tgt, "cpu")
+    sel, gt_of, best_q = cb.simota_batched(logits, boxes, gtb, gtl, ex)
+    assert torch.equal(sel[0], ind[0][0]) and torch.equal(gt_of[0][sel[0]], ind[0][1]) and torch.equal(best_q[0], mq[0])
+    assert int(sel.sum()) == 2
 
 
 def test_reference_state_dict_roundtrip():

@@ -28,6 +28,7 @@ from .. import _cabi
 from ..linear import linear as tc_linear
 from ..msda import MSDeformAttnFunction
 from . import criterion as crit
+from . import criterion_batched as critb
 from .state_spec import idol_r50_state_spec
 
 BB = "detr.detr.backbone.0.backbone."
@@ -136,7 +137,7 @@ class TcLinear(torch.autograd.Function):
 class IDOLTrainModel(nn.Module):
     def __init__(self, state_dict, device="cuda", num_classes=40, num_queries=300, dropout=0.1, freeze_at=2,
                  pixel_mean=(123.675, 116.280, 103.530), pixel_std=(58.395, 57.120, 57.375), mask_stride=4,
-                 weight_dict=None, heads=8, levels=4, points=4, precision="fp32"):
+                 weight_dict=None, heads=8, levels=4, points=4, precision="fp32", batched=True):
         super().__init__()
         if precision not in ("fp32", "tf32"):
             raise ValueError("precision must be 'fp32' (cuBLAS fp32 linears, strict parity) or 'tf32' (tcgen05 linears)")
@@ -167,6 +168,8 @@ class IDOLTrainModel(nn.Module):
         self.std = torch.tensor(pixel_std, device=self.device).view(1, 3, 1, 1)
         self.weight_dict = weight_dict or crit.default_weight_dict()
         self.criterion = crit.SetCriterion(num_classes, self.weight_dict, mask_out_stride=mask_stride)
+        self.batched = batched                   # device-batched assignment + losses (criterion_batched.py)
+        self.criterion_b = critb.BatchedCriterion(num_classes, mask_out_stride=mask_stride)
         self.enc_layers = 1 + max(int(k.split(".")[5]) for k in spec if k.startswith(TR + "encoder.layers."))
         self.dec_layers = 1 + max(int(k.split(".")[5]) for k in spec if k.startswith(TR + "decoder.layers."))
 
@@ -408,10 +411,78 @@ class IDOLTrainModel(nn.Module):
         x = self._aligned_bilinear(x.reshape(n, 1, h, w), stride // self.mask_stride)
         return x[:, 0]
 
+    def instance_masks_batched(self, feat, image_of, ref_px, params, stride=8, ch=8):
+        """feat [B,8,h,w]; image_of [n] long; ref_px [n,2]; params [n,169] -> logits [n, 2h, 2w] (all levels at once)."""
+        B, cin, h, w = feat.shape
+        n = ref_px.shape[0]
+        xs = torch.arange(0, w * stride, stride, dtype=torch.float32, device=feat.device) + stride // 2
+        ys = torch.arange(0, h * stride, stride, dtype=torch.float32, device=feat.device) + stride // 2
+        yy, xx = torch.meshgrid(ys, xs, indexing="ij")
+        loc = torch.stack((xx.reshape(-1), yy.reshape(-1)), 0)
+        x = torch.cat([ref_px[:, :, None] - loc[None], feat.flatten(2)[image_of]], 1)             # [n, 10, hw]
+        sizes = [(cin + 2) * ch, ch * ch, ch, ch, ch, 1]
+        w0, w1, w2, b0, b1, b2 = torch.split_with_sizes(params, sizes, dim=1)
+        x = F.relu(torch.baddbmm(b0[:, :, None], w0.reshape(n, ch, cin + 2), x))
+        x = F.relu(torch.baddbmm(b1[:, :, None], w1.reshape(n, ch, ch), x))
+        x = torch.baddbmm(b2[:, :, None], w2.reshape(n, 1, ch), x)
+        return self._aligned_bilinear(x.reshape(n, 1, h, w), stride // self.mask_stride)[:, 0]
+
     # ------------------------------------------------------------------ the training forward
     def forward(self, frames, det_targets, ref_targets):
         """-> (loss_dict unweighted, outputs).  frames [2B,3,H,W] or a list of 2B [3,h,w]; targets as
         IDOL.prepare_targets builds them."""
+        if self.batched:
+            return self.forward_batched(frames, det_targets, ref_targets)
+        return self.forward_sequential(frames, det_targets, ref_targets)
+
+    def forward_batched(self, frames, det_targets, ref_targets):
+        """All decoder levels' heads, assignments and losses as stacked tensors (criterion_batched.py)."""
+        d = self.dense(frames)
+        key, rf = slice(0, None, 2), slice(1, None, 2)
+        L = self.dec_layers
+        hs = torch.stack(d["hs"])                                                   # [L, N, nq, C]
+        hk = hs[:, key]
+        B, nq = hk.shape[1:3]
+        wc = torch.stack([self.P[f"{DETR}class_embed.{i}.weight"] for i in range(L)])
+        bc = torch.stack([self.P[f"{DETR}class_embed.{i}.bias"] for i in range(L)])
+        logits = torch.baddbmm(bc[:, None], hk.flatten(1, 2), wc.transpose(1, 2)).view(L, B, nq, -1)
+        boxes = torch.stack([c[key] for c in d["coords"]])
+        losses, assign = self.criterion_b.detection_losses(logits, boxes, det_targets)
+        # dynamic mask head for every selected (level, image, query) at once
+        sel = assign["sel"]
+        idx = torch.nonzero(sel)                                                    # the one sync listing the instances
+        l_i, b_i, q_i = idx.unbind(1)
+        scale = torch.tensor([[float(w), float(h)] for h, w in d["sizes"][key]], device=self.device)[:, None]
+        ref_px = torch.stack([inverse_sigmoid(r[key]).sigmoid()[..., :2] for r in d["level_ref"]]) * scale   # [L,B,nq,2]
+        feat = self.mask_features(d["memory"][key], d["shapes"], d["lsi"])
+        tm = self.criterion_b.mask_targets(det_targets, ref_targets, self.device)
+        if idx.shape[0] > 0:
+            params = self._mlp("detr.controller", hk[l_i, b_i, q_i])
+            ml = self.instance_masks_batched(feat, b_i, ref_px[l_i, b_i, q_i], params)
+            losses.update(self.criterion_b.mask_losses(ml, tm[b_i, assign["gt_of"][l_i, b_i, q_i]], l_i, L))
+        else:
+            z = (feat.sum() * 0).expand(L)
+            losses.update({"loss_mask": z, "loss_dice": z})
+        # contrastive reID terms (last level)
+        hs_key, hs_ref = hs[-1, key], hs[-1, rf]
+        ref_prob = self._lin(f"{DETR}class_embed.{L - 1}", hs_ref).sigmoid()
+        ke, re = self._mlp("detr.reid_embed_head", hs_key), self._mlp("detr.reid_embed_head", hs_ref)
+        reid = self.criterion_b.reid_losses(d["last_ref"][rf], ref_prob.detach(), ke, re, assign["best_q"][-1], ref_targets)
+        if reid is None:                                                            # repair-loop cases: sequential code
+            matched = [assign["best_q"][-1][b, :len(t["labels"])] for b, t in enumerate(det_targets)]
+            items = crit.select_pos_neg(d["last_ref"][rf], matched, ref_targets, det_targets, ke, re, ref_prob)
+            r = self.criterion.loss_reid({"pred_qd": items, "pred_logits": logits})
+            reid = (r["loss_reid"], r["loss_reid_aux"], len(items))
+        out = {}
+        for k, v in losses.items():
+            out[k] = v[L - 1]
+            for i in range(L - 1):
+                out[f"{k}_{i}"] = v[i]
+        out["loss_reid"], out["loss_reid_aux"] = reid[0], reid[1]
+        return out, {"pred_logits": logits[-1], "pred_boxes": boxes[-1], "assign": assign, "num_contrast_items": reid[2]}
+
+    def forward_sequential(self, frames, det_targets, ref_targets):
+        """The reference's control flow level by level (criterion.py) — the parity anchor for forward_batched."""
         d = self.dense(frames)
         key, rf = slice(0, None, 2), slice(1, None, 2)
         scale = torch.tensor([[float(w), float(h)] for h, w in d["sizes"][key]], device=self.device)[:, None]  # segm:177-181
