@@ -50,5 +50,17 @@ def test_idol_facade_chunks_long_videos():
     m.batch_infer_len = 10
     whole = m.dense_forward([{"image": frames, "height": 96, "width": 128}])
     assert _rel(out["pred_logits"], whole["pred_logits"]) < 1e-4      # frames are independent
-    with pytest.raises(NotImplementedError, match="tracker"):
-        m([{"image": frames, "height": 96, "width": 128}])
+    res = m([{"image": frames, "height": 72, "width": 100}])        # full eval forward: dense path + online tracker
+    assert set(res) == {"image_size", "pred_scores", "pred_labels", "pred_masks"} and res["image_size"] == (72, 100)
+    assert len(res["pred_scores"]) == len(res["pred_labels"]) == len(res["pred_masks"])
+    for per_frame in res["pred_masks"]:
+        assert len(per_frame) == 5 and all(x is None or tuple(x.shape) == (72, 100) for x in per_frame)
+    seen = []
+    m.tracker_fn = lambda out, ori, img: seen.append((ori, img, out["pred_logits"].shape)) or "mine"
+    assert m([{"image": frames, "height": 72, "width": 100}]) == "mine" and seen == [((72, 100), (96, 128), (5, 300, 40))]
+
+
+@pytest.mark.parametrize("name", ["default", "seed1", "nofw"])
+def test_tracker_on_device_matches_reference(name):
+    from test_idol_tracker_golden import check_case
+    check_case(name, "cuda")

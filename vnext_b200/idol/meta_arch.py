@@ -1,8 +1,8 @@
 """`IDOL` META_ARCH facade (projects/IDOL/idol/idol.py:71-295): same cfg keys and `batched_inputs`; the dense
-per-frame path runs on the B200 engine in chunks of BATCH_INFER_LEN frames (idol.py:252-274).  The online tracker
-(`IDOL_Tracker`, idol.py:275-295 / models/tracker.py) is host-side association and is NOT part of this round's path
-(SURVEY §8f): in eval mode `forward` hands the dense outputs to `self.tracker_fn(output, (height, width), image_size)` when one is
-attached (e.g. the reference's own `IDOL.inference` bound to its tracker) and raises otherwise; `dense_forward`
+per-frame path runs on the B200 engine in chunks of BATCH_INFER_LEN frames (idol.py:252-274).  In eval mode `forward`
+then runs the online association + video post-processing of idol.py:275-295 / :326-473 (vnext_b200/idol/tracker.py:
+batched device ops + host bookkeeping, pinned to the reference's own outputs), or hands the dense outputs to
+`self.tracker_fn(output, (height, width), image_size)` when one is attached (e.g. the reference's `IDOL.inference`); `dense_forward`
 returns exactly what the reference's `detr.inference_forward` returns.  In training mode `forward` returns the weighted
 loss dict of idol.py:205-215 from the differentiable dense path (vnext_b200/idol/train.py: MSDA forward/backward
 kernels under autograd) and the host-side criterion (criterion.py)."""
@@ -28,6 +28,15 @@ class IDOL(nn.Module):
         self.precision = precision
         self.tracker_fn = tracker_fn
         self.dropout = g("MODEL.IDOL.DROPOUT", 0.1)
+        self.is_multi_cls = g("MODEL.IDOL.MULTI_CLS_ON", True)                  # evaluation keys, idol/config.py:51-65
+        self.apply_cls_thres = g("MODEL.IDOL.APPLY_CLS_THRES", 0.05)
+        self.temporal_score_type = g("MODEL.IDOL.TEMPORAL_SCORE_TYPE", "mean")
+        self.inference_select_thres = g("MODEL.IDOL.INFERENCE_SELECT_THRES", 0.1)
+        self.inference_fw = g("MODEL.IDOL.INFERENCE_FW", True)
+        self.inference_tw = g("MODEL.IDOL.INFERENCE_TW", True)
+        self.memory_len = g("MODEL.IDOL.MEMORY_LEN", 3)
+        self.nms_pre = g("MODEL.IDOL.NMS_PRE", 0.5)
+        self.add_new_score = g("MODEL.IDOL.ADD_NEW_SCORE", 0.2)
         from .criterion import default_weight_dict
         self.weight_dict = default_weight_dict(g("MODEL.IDOL.CLASS_WEIGHT", 2.0), g("MODEL.IDOL.L1_WEIGHT", 5.0),
                                                g("MODEL.IDOL.GIOU_WEIGHT", 2.0), g("MODEL.IDOL.REID_WEIGHT", 2.0),
@@ -114,12 +123,19 @@ class IDOL(nn.Module):
             loss_dict, _ = model(frames, det, ref)
             return model.weighted(loss_dict)
         output = self.dense_forward(batched_inputs)
-        if self.tracker_fn is None:
-            raise NotImplementedError("IDOL's online tracker (models/tracker.py) is host-side post-processing outside "
-                                      "this round's path; attach tracker_fn or use dense_forward()")
         v = batched_inputs[0]
         H, W = v["image"][0].shape[-2:]
-        return self.tracker_fn(output, (v.get("height", H), v.get("width", W)), (H, W))
+        ori_size, image_size = (v.get("height", H), v.get("width", W)), (H, W)
+        if self.tracker_fn is not None:                      # e.g. the reference's own IDOL.inference bound to its tracker
+            return self.tracker_fn(output, ori_size, image_size)
+        from .tracker import IDOLTracker, video_inference
+        tracker = IDOLTracker(init_score_thr=0.2, obj_score_thr=0.1, nms_thr_pre=self.nms_pre, nms_thr_post=0.05,
+                              addnew_score_thr=self.add_new_score, memo_tracklet_frames=10, memo_momentum=0.8,
+                              long_match=self.inference_tw, frame_weight=(self.inference_tw | self.inference_fw),
+                              temporal_weight=self.inference_tw, memory_len=self.memory_len)        # idol.py:276-290
+        return video_inference(output, tracker, ori_size, image_size, select_thres=self.inference_select_thres,
+                               temporal_score_type=self.temporal_score_type, multi_cls=self.is_multi_cls,
+                               apply_cls_thres=self.apply_cls_thres, mask_stride=self.mask_stride)
 
 
 def register_with_detectron2():

@@ -128,6 +128,54 @@ def synthetic_targets(num_videos, height, width, seed=0, insts=3, num_classes=40
     return det, ref
 
 
+def synthetic_track_outputs(num_frames=14, num_queries=40, num_classes=40, embed_dim=32, h=24, w=32, seed=0):
+    """Dense per-frame outputs (`detr.inference_forward` format, projects/IDOL/idol/models/segmentation_condInst.py:
+    233-321) of a scripted video for exercising the online tracker: 4 objects drifting across the frame, one of them
+    hidden for three frames, one entering late, duplicate detections (mask-NMS fodder), low-score clutter, and one
+    frame where nothing passes INFERENCE_SELECT_THRES (the top-1 fallback, idol.py:355-358).  Detections land in a
+    different query slot every frame."""
+    g = _gen("track", seed)
+    T, nq, K, C = num_frames, num_queries, num_classes, embed_dim
+    logits = torch.full((T, nq, K), -6.0) + torch.randn(T, nq, K, generator=g) * 0.2
+    boxes = torch.rand(T, nq, 4, generator=g) * 0.1 + torch.tensor([0.45, 0.45, 0.02, 0.02])
+    embeds = torch.randn(T, nq, C, generator=g) * 0.3
+    masks = torch.full((T, nq, 1, h, w), -4.0) + torch.randn(T, nq, 1, h, w, generator=g) * 0.3
+    n_obj = 4
+    ident = torch.nn.functional.normalize(torch.randn(n_obj, C, generator=g), dim=1) * 4.0
+    cls = torch.randint(0, K, (n_obj,), generator=g)
+    start = torch.rand(n_obj, 2, generator=g) * 0.5 + 0.2
+    vel = (torch.rand(n_obj, 2, generator=g) - 0.5) * 0.03
+    size = torch.rand(n_obj, 2, generator=g) * 0.15 + 0.15
+    ys, xs = torch.arange(h).view(h, 1), torch.arange(w).view(1, w)
+
+    def paint(t, q, c, wh, score, k, noise=0.15):
+        logits[t, q, cls[k]] = torch.logit(torch.tensor(score))
+        logits[t, q, (cls[k] + 1) % K] = torch.logit(torch.tensor(score * 0.3))
+        boxes[t, q] = torch.cat([c, wh])
+        embeds[t, q] = ident[k] + torch.randn(C, generator=g) * noise
+        x0, x1 = (c[0] - wh[0] / 2) * w, (c[0] + wh[0] / 2) * w
+        y0, y1 = (c[1] - wh[1] / 2) * h, (c[1] + wh[1] / 2) * h
+        inside = (xs >= x0) & (xs < x1) & (ys >= y0) & (ys < y1)
+        masks[t, q, 0] = torch.where(inside, torch.tensor(4.0), torch.tensor(-4.0)) + torch.randn(h, w, generator=g) * 0.3
+
+    for t in range(T):
+        if t == 11:
+            continue                                       # nothing confident in this frame
+        slots = torch.randperm(nq, generator=g).tolist()
+        for k in range(n_obj):
+            if (k == 2 and 5 <= t <= 7) or (k == 3 and t < 4):
+                continue
+            c = (start[k] + vel[k] * t).clamp(0.1, 0.9)
+            score = float(0.45 + 0.4 * torch.rand((), generator=g))
+            paint(t, slots.pop(), c, size[k], score, k)
+            if (t + k) % 3 == 0:                           # a duplicate of the same object, slightly off, lower score
+                paint(t, slots.pop(), c + 0.01, size[k] * 0.95, score * 0.6, k, noise=0.4)
+        for _ in range(2):                                 # weak clutter just above the selection threshold
+            q = slots.pop()
+            logits[t, q, int(torch.randint(0, K, (), generator=g))] = torch.logit(torch.tensor(0.13))
+    return {"pred_logits": logits, "pred_boxes": boxes, "pred_inst_embed": embeds, "pred_masks": masks}
+
+
 def make_msda_inputs(N, Lq, M, D, shapes, P, seed, dtype=torch.float32, loc_range=(0.0, 1.0)):
     """MSDA input recipe of the reference test (projects/IDOL/idol/models/ops/test.py:33-36):
     value ~ U(0, .01), sampling locations ~ U(loc_range), attention weights normalised over (L, P)."""
