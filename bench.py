@@ -281,6 +281,8 @@ def own_arm(args, rank, world, local_rank):
             m = fam["msda_fwd_tile_kernel"]
             roofline["msda"] = {"achieved": round(m["bytes"] / m["us"] / 1e3, 1), "frac": round(m["bytes"] / m["us"] / 1e3 / hbm, 4),
                                 "us_per_step": round(m["us"] / 3, 1)}
+            if args.workload == "720p":        # dram__bytes_read+write of one encoder launch (350.5 MB algorithmic), ncu --set full
+                roofline["msda"].update(traffic=341668096, traffic_source="profiles/r01_msda_enc_v3_ncu_full.txt")
 
     cpu = None
     if args.gpus == 1 and not args.no_cpu_baseline and swin is None:
