@@ -65,6 +65,11 @@ def test_graph_runner_and_meta_arch_output():
     agree = np.mean([(a == b).float().mean().item() for a, b in zip(got["pred_masks"], want["pred_masks"])])
     assert agree > 0.999
     assert all(torch.equal(a, b) for a, b in zip(got["pred_masks"], got2["pred_masks"]))
+    # results are fresh tensors: a later clip must not overwrite an earlier clip's masks (the reference returns new ones)
+    snapshot = [m.clone() for m in got["pred_masks"]]
+    other = model([{"image": synthetic_clip(T, H, W, seed + 7), "height": H, "width": W, "file_names": ["a", "b", "c"]}])
+    assert all(torch.equal(a, b) for a, b in zip(got["pred_masks"], snapshot))
+    assert other["pred_masks"][0].data_ptr() != got["pred_masks"][0].data_ptr()
     with pytest.raises(KeyError):
         SeqFormer(state_dict={k: v for k, v in sd.items() if "query_embed" not in k}, device="cuda")
 

@@ -28,10 +28,8 @@ class ClipRunner:
                 self.graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self.graph, stream=self.stream):
                     self.scores, self.masks = self._device_step()
-        self.scores_pin = torch.empty(self.scores.shape, dtype=self.scores.dtype).pin_memory()
-        self.masks_pin = torch.empty(self.masks.shape, dtype=self.masks.dtype).pin_memory()
         self.h2d_bytes = self.frames_pin.numel()
-        self.d2h_bytes = self.scores_pin.numel() * 4 + self.masks_pin.numel()
+        self.d2h_bytes = self.scores.numel() * 4 + self.masks.numel()
 
     def _device_step(self):
         return self.engine.infer_video_device(self.frames_dev, self.ori_size, self.topk)   # uint8 in, fused normalise
@@ -45,13 +43,17 @@ class ClipRunner:
                 self.scores, self.masks = self._device_step()
 
     def run_host(self, frames_u8=None):
-        """End to end: pinned host frames -> device -> graph -> pinned host outputs (+ sync)."""
+        """End to end: pinned host frames -> device -> graph -> pinned host outputs (+ sync).  The outputs are FRESH
+        pinned tensors every call (PyTorch's caching host allocator recycles a block only after the caller dropped it),
+        so results of earlier clips are never overwritten — the reference returns new tensors too."""
         if frames_u8 is not None:
             self.frames_pin.copy_(frames_u8)
+        scores_pin = torch.empty(self.scores.shape, dtype=self.scores.dtype, pin_memory=True)
+        masks_pin = torch.empty(self.masks.shape, dtype=self.masks.dtype, pin_memory=True)
         with torch.cuda.stream(self.stream):
             self.frames_dev.copy_(self.frames_pin, non_blocking=True)
             self.run_device()
-            self.scores_pin.copy_(self.scores, non_blocking=True)
-            self.masks_pin.copy_(self.masks, non_blocking=True)
+            scores_pin.copy_(self.scores, non_blocking=True)
+            masks_pin.copy_(self.masks, non_blocking=True)
         self.stream.synchronize()
-        return self.scores_pin, self.masks_pin
+        return scores_pin, masks_pin
