@@ -17,7 +17,7 @@ if os.environ.get("CUDNN_BENCH"):
 NF, H, W = 8, 480, 864
 PREC = os.environ.get("PREC", "fp32")
 dev = torch.device("cuda")
-model = T.IDOLTrainModel(fill_state_dict(idol_r50_state_spec(), 0), device=dev, dropout=0.1, precision=PREC).train()
+model = T.IDOLTrainModel(fill_state_dict(idol_r50_state_spec(), 0), device=dev, dropout=0.1, precision=PREC, channels_last=os.environ.get("CL", "1") == "1").train()
 trainer = T.IDOLTrainer(model)
 frames = torch.stack(synthetic_clip(NF, H, W, 0)).to(dev)
 det, ref = synthetic_targets(NF // 2, H, W, 0)

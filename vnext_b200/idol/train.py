@@ -137,11 +137,13 @@ class TcLinear(torch.autograd.Function):
 class IDOLTrainModel(nn.Module):
     def __init__(self, state_dict, device="cuda", num_classes=40, num_queries=300, dropout=0.1, freeze_at=2,
                  pixel_mean=(123.675, 116.280, 103.530), pixel_std=(58.395, 57.120, 57.375), mask_stride=4,
-                 weight_dict=None, heads=8, levels=4, points=4, precision="fp32", batched=True):
+                 weight_dict=None, heads=8, levels=4, points=4, precision="fp32", batched=True,
+                 channels_last=True):
         super().__init__()
         if precision not in ("fp32", "tf32"):
             raise ValueError("precision must be 'fp32' (cuBLAS fp32 linears, strict parity) or 'tf32' (tcgen05 linears)")
         self.tc = precision == "tf32"
+        self.cl = channels_last               # NHWC activations / weights for cuDNN; tokens become free views of them
         if self.tc:                                   # weight-gradient GEMMs (cuBLAS) in TF32 as well; process-global flag
             torch.backends.cuda.matmul.allow_tf32 = True
         self.device = torch.device(device)
@@ -202,11 +204,16 @@ class IDOLTrainModel(nn.Module):
             x = self._lin(f"{p}.layers.{i}", x, relu=i < n - 1)
         return x
 
+    def _conv2d(self, x, w, b, stride=1, padding=0):
+        if self.cl:
+            w = w.contiguous(memory_format=torch.channels_last)
+        return F.conv2d(x, w, b, stride=stride, padding=padding)
+
     def _conv_bn(self, p, x, stride=1, padding=0, relu=True):
         n = p + ".norm."
         scale = self.P[n + "weight"] * torch.rsqrt(self.P[n + "running_var"] + 1e-5)      # batch_norm.py:48-53
         shift = self.P[n + "bias"] - self.P[n + "running_mean"] * scale
-        x = F.conv2d(x, self.P[p + ".weight"] * scale.view(-1, 1, 1, 1), shift, stride=stride, padding=padding)
+        x = self._conv2d(x, self.P[p + ".weight"] * scale.view(-1, 1, 1, 1), shift, stride=stride, padding=padding)
         return F.relu(x, inplace=True) if relu else x
 
     # ------------------------------------------------------------------ backbone (resnet.py:194-210, 355-359, 435-458)
@@ -294,18 +301,20 @@ class IDOLTrainModel(nn.Module):
             h, w = sizes[i]
             x[i, :, :h, :w] = (f.to(self.device, torch.float32) - self.mean[0]) / self.std[0]
             mask[i, :h, :w] = False
+        if self.cl:
+            x = x.contiguous(memory_format=torch.channels_last)
         feats = self.backbone(x)
         srcs, masks, poses = [], [], []
         for l, name in enumerate(("res3", "res4", "res5", "res5")):
             k = 3 if l == 3 else 1
-            s = F.conv2d(feats[name], self.P[f"{DETR}input_proj.{l}.0.weight"], self.P[f"{DETR}input_proj.{l}.0.bias"],
+            s = self._conv2d(feats[name], self.P[f"{DETR}input_proj.{l}.0.weight"], self.P[f"{DETR}input_proj.{l}.0.bias"],
                          stride=2 if l == 3 else 1, padding=k // 2)
             s = F.group_norm(s, 32, self.P[f"{DETR}input_proj.{l}.1.weight"], self.P[f"{DETR}input_proj.{l}.1.bias"], 1e-5)
             with torch.no_grad():
                 # level masks: nearest-resized padding mask; level 3 resizes masks[0] (segm:117-118)
                 m = F.interpolate((mask if l < 3 else masks[0])[None].float(), size=s.shape[-2:]).to(torch.bool)[0]
                 pos = self._sine_pos(m).flatten(1, 2)
-            srcs.append(s.flatten(2).transpose(1, 2))
+            srcs.append(s.permute(0, 2, 3, 1).flatten(1, 2))                       # a view when s is channels-last
             masks.append(m)
             poses.append(pos + self.P[TR + "level_embed"][l].view(1, 1, -1))
         shapes = torch.as_tensor([m.shape[-2:] for m in masks], dtype=torch.long, device=self.device)
@@ -362,7 +371,7 @@ class IDOLTrainModel(nn.Module):
 
     # ------------------------------------------------------------------ mask branch + dynamic head (segm:324-374, 376-470, 539-575)
     def _conv(self, p, x):
-        return F.conv2d(x, self.P[p + ".weight"], self.P[p + ".bias"], padding=1)
+        return self._conv2d(x, self.P[p + ".weight"], self.P[p + ".bias"], padding=1)
 
     def mask_features(self, memory, shapes, lsi):
         lv = []
