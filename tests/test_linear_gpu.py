@@ -15,7 +15,7 @@ def _mk(M, N, K, seed=0):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 256), (300, 256, 256), (1000, 384, 256), (97800, 256, 256),
-                                   (4097, 1024, 256), (513, 256, 1024), (77, 64, 64), (1500, 128, 2048), (5, 169, 256)])
+                                   (4097, 1024, 256), (513, 256, 1024), (77, 64, 64), (1500, 128, 2048), (5, 169, 256), (2000, 640, 256), (300, 384, 64)])
 def test_bias_and_relu(M, N, K):
     from vnext_b200.linear import linear
     torch.backends.cuda.matmul.allow_tf32 = False
