@@ -87,3 +87,36 @@ def test_tf32_mode_error_is_reported():
     errs = {k: _rel(out[k].cpu(), ref[k]) for k in ("pred_logits", "pred_boxes", "pred_masks")}
     print("tf32 relative errors:", errs)
     assert max(errs.values()) < 2e-2
+
+
+def test_clip_matching_inference_long_video():
+    """CLIP_MATCHING: True — sliding clips through the engine, stitched on the device; against the CPU oracle run on the
+    same windows + the (reference-pinned) clip tracker."""
+    from vnext_b200.seqformer.clip_matching import (ClipTracks, clip_matching_postprocess, clip_windows,
+                                                    select_clip_instances)
+    from vnext_b200.seqformer.meta_arch import SeqFormer
+    L, H, W = 5, 96, 128
+    sd = fill_state_dict(seqformer_r50_state_spec(), 0)
+    frames = synthetic_clip(L, H, W, 4)
+    model = SeqFormer(state_dict=sd, device="cuda", precision="fp32").eval()
+    model.clip_matching, model.clip_length, model.clip_stride = True, 3, 1
+    got = model([{"image": frames, "height": H, "width": W, "file_names": [str(i) for i in range(L)]}])
+    tracks = None
+    with torch.no_grad():
+        for idx in clip_windows(L, 3, 1):
+            o = SO.inference(sd, [frames[i] for i in idx])
+            cls, ml = select_clip_instances(o["pred_logits"], o["pred_masks"])
+            if tracks is None:
+                tracks = ClipTracks(3, L, 40, tuple(ml.shape[-2:]), "cpu")
+            tracks.update(idx, cls, ml)
+        want = clip_matching_postprocess(*tracks.get_result(), (H, W), (H, W))
+    assert got["pred_labels"] == want["pred_labels"] and got["image_size"] == (H, W)
+    assert torch.allclose(torch.tensor(got["pred_scores"]), torch.tensor(want["pred_scores"]), rtol=1e-3, atol=1e-4)
+    agree = np.mean([(a == b).float().mean().item() for a, b in zip(got["pred_masks"], want["pred_masks"])])
+    assert agree > 0.999 and got["pred_masks"][0].shape == (L, H, W)
+
+
+@pytest.mark.parametrize("name", ["stride1", "stride3", "short"])
+def test_clip_tracker_on_device_matches_reference(name):
+    from test_seqformer_clipmatch_golden import run_case
+    run_case(name, "cuda")

@@ -42,6 +42,12 @@ class IDOL(nn.Module):
                                                g("MODEL.IDOL.GIOU_WEIGHT", 2.0), g("MODEL.IDOL.REID_WEIGHT", 2.0),
                                                g("MODEL.IDOL.MASK_WEIGHT", 2.0), g("MODEL.IDOL.DICE_WEIGHT", 5.0),
                                                g("MODEL.IDOL.DEC_LAYERS", 6), g("MODEL.IDOL.DEEP_SUPERVISION", True))
+        # backbone: build_resnet_backbone (R50) or D2SwinTransformer (cfg.MODEL.SWIN.*, I/config.py, configs/*swinL.yaml)
+        self.swin = None
+        if "swin" in str(g("MODEL.BACKBONE.NAME", "build_resnet_backbone")).lower():
+            self.swin = dict(embed_dim=g("MODEL.SWIN.EMBED_DIM", 96), depths=tuple(g("MODEL.SWIN.DEPTHS", (2, 2, 6, 2))),
+                             num_heads=tuple(g("MODEL.SWIN.NUM_HEADS", (3, 6, 12, 24))),
+                             window_size=g("MODEL.SWIN.WINDOW_SIZE", 7))
         self.engine = None
         self._state_dict = None
         self._train_model = None
@@ -52,12 +58,13 @@ class IDOL(nn.Module):
         self._state_dict = state_dict
         if not keep_train_model:
             self._train_model = None
-        spec = idol_r50_state_spec(self.num_queries, self.num_classes)
+        spec = idol_r50_state_spec(self.num_queries, self.num_classes, swin=self.swin)
         missing = [k for k in spec if k not in state_dict]
         if missing:
             raise KeyError(f"checkpoint is missing {len(missing)} keys, e.g. {missing[:3]}")
         self.engine = IDOLEngine(state_dict, device=self.device_name, pixel_mean=self.pixel_mean,
-                                 pixel_std=self.pixel_std, mask_stride=self.mask_stride, precision=self.precision)
+                                 pixel_std=self.pixel_std, mask_stride=self.mask_stride, precision=self.precision,
+                                 swin=self.swin)
 
     @torch.no_grad()
     def dense_forward(self, batched_inputs):
@@ -80,6 +87,9 @@ class IDOL(nn.Module):
         if self._train_model is None:
             if self._state_dict is None:
                 raise RuntimeError("no weights loaded: call load_reference_state_dict(checkpoint['model'])")
+            if self.swin is not None:
+                raise NotImplementedError("the training path is built for the ResNet-50 backbone (BASELINE config 3); "
+                                          "Swin training needs the window-attention backward, not built this round")
             from .train import IDOLTrainModel
             self._train_model = IDOLTrainModel(self._state_dict, device=self.device_name, num_classes=self.num_classes,
                                                num_queries=self.num_queries, dropout=self.dropout,

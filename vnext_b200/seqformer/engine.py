@@ -623,6 +623,20 @@ class SeqFormerEngine:
             pm = F.interpolate(pm, size=tuple(ori_size), mode="nearest")
         return scores[idx], pm > 0.5
 
+    @torch.no_grad()
+    def infer_clip_device(self, frames, topk=10):
+        """One clip of CLIP_MATCHING inference: the dense path + `inference_clip`'s top-k selection (seqformer.py:
+        310-334).  -> (cls_probs [k, K], mask_logits [k, T, H/4, W/4]) on the device."""
+        self._flags()
+        T, _, H, W = frames.shape
+        plan = self.plan(T, H, W)
+        memory = self.encoder(self.tokens(self.backbone(self.preprocess(frames, plan)), plan), plan)
+        level = self.decoder(memory, plan)[-1]
+        logits, boxes, params, ref_px = self.heads(level, plan)
+        scores = logits[0].sigmoid()
+        _, idx = torch.topk(scores.max(1)[0], k=min(topk, scores.shape[0]))
+        return scores[idx], self.dynamic_masks(self.mask_features(memory, plan), params[idx], ref_px[:, idx])
+
     @staticmethod
     def finish_video(valid_scores, masks, ori_size, apply_cls_thres=0.05, multi_cls=True):
         """Host part of whole_video_inference (seqformer.py:383-409): thresholding and list building."""

@@ -27,6 +27,8 @@ class SeqFormer(nn.Module):
         self.is_multi_cls = g("MODEL.SeqFormer.MULTI_CLS_ON", True)
         self.apply_cls_thres = g("MODEL.SeqFormer.APPLY_CLS_THRES", 0.05)
         self.clip_matching = g("MODEL.SeqFormer.CLIP_MATCHING", False)
+        self.clip_length = g("MODEL.SeqFormer.CLIP_LENGTH", 5)          # S/config.py:58-60
+        self.clip_stride = g("MODEL.SeqFormer.CLIP_STRIDE", 1)
         self.pixel_mean = tuple(g("MODEL.PIXEL_MEAN", (123.675, 116.280, 103.530)))
         self.pixel_std = tuple(g("MODEL.PIXEL_STD", (58.395, 57.120, 57.375)))
         self.device_name = g("MODEL.DEVICE", device)
@@ -73,19 +75,42 @@ class SeqFormer(nn.Module):
             raise NotImplementedError("vnext_b200 SeqFormer: the training step is not on this round's hot path")
         if self.engine is None:
             raise RuntimeError("no weights loaded: call load_reference_state_dict(checkpoint['model'])")
-        if self.clip_matching:
-            raise NotImplementedError("CLIP_MATCHING inference (seqformer.py:236-262) is out of scope (SURVEY §8f)")
         video = batched_inputs[0]
         frames = video["image"]
         T = len(frames)
         H, W = frames[0].shape[-2:]
         ori = (video.get("height", H), video.get("width", W))
+        if self.clip_matching:
+            return self._forward_clip_matching(frames, ori)
         run = self.runner(T, H, W, ori)
         stage = run.frames_pin
         for i, f in enumerate(frames):              # uint8-valued frames (float or uint8 tensors) -> pinned staging
             stage[i].copy_(f)
         scores, masks = run.run_host()
         return SeqFormerEngine.finish_video(scores, masks, ori, self.apply_cls_thres, self.is_multi_cls)
+
+
+def _clip_matching_forward(self, frames, ori):
+    """Long videos: sliding clips stitched by mask overlap (seqformer.py:236-262; clip_matching.py)."""
+    from .clip_matching import ClipTracks, clip_matching_postprocess, clip_windows
+    L = len(frames)
+    H, W = frames[0].shape[-2:]
+    dev = self.engine.device
+    tracks = None
+    for frame_idx in clip_windows(L, self.clip_length, self.clip_stride):
+        clip = torch.stack([frames[i] for i in frame_idx]).to(dev, non_blocking=True)
+        if clip.dtype not in (torch.uint8, torch.float32):
+            clip = clip.float()
+        cls, logits = self.engine.infer_clip_device(clip)
+        if tracks is None:
+            tracks = ClipTracks(self.clip_length, L, self.num_classes, tuple(logits.shape[-2:]), dev)
+        tracks.update(frame_idx, cls, logits)
+    pred_cls, pred_logits = tracks.get_result()
+    return clip_matching_postprocess(pred_cls, pred_logits, ori, (H, W), self.mask_stride, self.is_multi_cls,
+                                     self.apply_cls_thres)
+
+
+SeqFormer._forward_clip_matching = _clip_matching_forward
 
 
 def _cfg_get(cfg, path, default):

@@ -176,6 +176,54 @@ def synthetic_track_outputs(num_frames=14, num_queries=40, num_classes=40, embed
     return {"pred_logits": logits, "pred_boxes": boxes, "pred_inst_embed": embeds, "pred_masks": masks}
 
 
+def synthetic_clip_outputs(video_length=9, clip_length=5, stride=1, num_queries=30, num_classes=40, h=12, w=16, seed=0):
+    """Per-clip dense outputs of SeqFormer (`CondInst_segm.inference`: pred_logits [1,nq,K], pred_masks [1,nq,T,h,w])
+    for every window that CLIP_MATCHING inference visits (projects/SeqFormer/seqformer/seqformer.py:236-262), from a
+    scripted video with 3 moving objects (one enters late) + clutter.  Objects land in different query slots in every
+    clip, so the clips can only be stitched by mask overlap.  -> list of (frame_idx list, outputs dict)."""
+    g = _gen("clips", seed)
+    n_obj, K = 3, num_classes
+    cls = torch.randint(0, K, (n_obj,), generator=g)
+    start = torch.rand(n_obj, 2, generator=g) * 0.5 + 0.2
+    vel = (torch.rand(n_obj, 2, generator=g) - 0.5) * 0.06
+    size = torch.rand(n_obj, 2, generator=g) * 0.2 + 0.2
+    ys, xs = torch.arange(h).view(h, 1), torch.arange(w).view(1, w)
+    windows, last = [], False
+    for s0 in range(0, video_length, stride):
+        e0 = s0 + clip_length
+        if e0 >= video_length:
+            last = True
+            s0, e0 = max(0, video_length - clip_length), video_length
+        windows.append(list(range(s0, e0)))
+        if last:
+            break
+    out = []
+    for frames in windows:
+        T = len(frames)
+        logits = torch.full((1, num_queries, K), -6.0) + torch.randn(1, num_queries, K, generator=g) * 0.2
+        masks = torch.full((1, num_queries, T, h, w), -5.0) + torch.randn(1, num_queries, T, h, w, generator=g) * 0.3
+        slots = torch.randperm(num_queries, generator=g).tolist()
+        for k in range(n_obj):
+            if k == 2 and frames[-1] < 3:
+                continue                                   # third object enters at frame 3
+            q = slots.pop()
+            score = float(0.5 + 0.4 * torch.rand((), generator=g))
+            logits[0, q, cls[k]] = torch.logit(torch.tensor(score))
+            logits[0, q, (cls[k] + 3) % K] = torch.logit(torch.tensor(score * 0.2))
+            for ti, f in enumerate(frames):
+                if k == 2 and f < 3:
+                    continue
+                c = (start[k] + vel[k] * f).clamp(0.1, 0.9)
+                inside = (xs >= (c[0] - size[k, 0] / 2) * w) & (xs < (c[0] + size[k, 0] / 2) * w) & \
+                         (ys >= (c[1] - size[k, 1] / 2) * h) & (ys < (c[1] + size[k, 1] / 2) * h)
+                masks[0, q, ti] = torch.where(inside, torch.tensor(5.0), torch.tensor(-5.0)) + \
+                    torch.randn(h, w, generator=g) * 0.3
+        for _ in range(3):                                 # clutter that still makes the top-10
+            logits[0, slots.pop(), int(torch.randint(0, K, (), generator=g))] = torch.logit(torch.tensor(0.08))
+        out.append((frames, {"pred_logits": logits, "pred_masks": masks}))
+    return out
+
+
 def make_msda_inputs(N, Lq, M, D, shapes, P, seed, dtype=torch.float32, loc_range=(0.0, 1.0)):
     """MSDA input recipe of the reference test (projects/IDOL/idol/models/ops/test.py:33-36):
     value ~ U(0, .01), sampling locations ~ U(loc_range), attention weights normalised over (L, P)."""
