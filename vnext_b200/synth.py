@@ -179,7 +179,8 @@ def synthetic_track_outputs(num_frames=14, num_queries=40, num_classes=40, embed
 def synthetic_clip_outputs(video_length=9, clip_length=5, stride=1, num_queries=30, num_classes=40, h=12, w=16, seed=0):
     """Per-clip dense outputs of SeqFormer (`CondInst_segm.inference`: pred_logits [1,nq,K], pred_masks [1,nq,T,h,w])
     for every window that CLIP_MATCHING inference visits (projects/SeqFormer/seqformer/seqformer.py:236-262), from a
-    scripted video with 3 moving objects (one enters late) + clutter.  Objects land in different query slots in every
+    scripted video with 3 moving objects (one enters late) + clutter (background logits -9, so every soft IoU is either
+    large or orders of magnitude below the 0.01 match threshold: no borderline decisions for float noise to flip).  Objects land in different query slots in every
     clip, so the clips can only be stitched by mask overlap.  -> list of (frame_idx list, outputs dict)."""
     g = _gen("clips", seed)
     n_obj, K = 3, num_classes
@@ -201,7 +202,7 @@ def synthetic_clip_outputs(video_length=9, clip_length=5, stride=1, num_queries=
     for frames in windows:
         T = len(frames)
         logits = torch.full((1, num_queries, K), -6.0) + torch.randn(1, num_queries, K, generator=g) * 0.2
-        masks = torch.full((1, num_queries, T, h, w), -5.0) + torch.randn(1, num_queries, T, h, w, generator=g) * 0.3
+        masks = torch.full((1, num_queries, T, h, w), -9.0) + torch.randn(1, num_queries, T, h, w, generator=g) * 0.3
         slots = torch.randperm(num_queries, generator=g).tolist()
         for k in range(n_obj):
             if k == 2 and frames[-1] < 3:
@@ -216,7 +217,7 @@ def synthetic_clip_outputs(video_length=9, clip_length=5, stride=1, num_queries=
                 c = (start[k] + vel[k] * f).clamp(0.1, 0.9)
                 inside = (xs >= (c[0] - size[k, 0] / 2) * w) & (xs < (c[0] + size[k, 0] / 2) * w) & \
                          (ys >= (c[1] - size[k, 1] / 2) * h) & (ys < (c[1] + size[k, 1] / 2) * h)
-                masks[0, q, ti] = torch.where(inside, torch.tensor(5.0), torch.tensor(-5.0)) + \
+                masks[0, q, ti] = torch.where(inside, torch.tensor(5.0), torch.tensor(-9.0)) + \
                     torch.randn(h, w, generator=g) * 0.3
         for _ in range(3):                                 # clutter that still makes the top-10
             logits[0, slots.pop(), int(torch.randint(0, K, (), generator=g))] = torch.logit(torch.tensor(0.08))
