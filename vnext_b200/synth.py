@@ -219,8 +219,9 @@ def synthetic_clip_outputs(video_length=9, clip_length=5, stride=1, num_queries=
                          (ys >= (c[1] - size[k, 1] / 2) * h) & (ys < (c[1] + size[k, 1] / 2) * h)
                 masks[0, q, ti] = torch.where(inside, torch.tensor(5.0), torch.tensor(-9.0)) + \
                     torch.randn(h, w, generator=g) * 0.3
-        for _ in range(3):                                 # clutter that still makes the top-10
-            logits[0, slots.pop(), int(torch.randint(0, K, (), generator=g))] = torch.logit(torch.tensor(0.08))
+        for j in range(3):                                 # clutter that still makes the top-10 (distinct scores: no
+            score = 0.08 - 0.005 * j                       # top-k ties, whose order is implementation-defined)
+            logits[0, slots.pop(), int(torch.randint(0, K, (), generator=g))] = torch.logit(torch.tensor(score))
         out.append((frames, {"pred_logits": logits, "pred_masks": masks}))
     return out
 
