@@ -212,7 +212,8 @@ def own_arm(args, rank, world, local_rank):
     fps = world * args.steps * T / (ms_total / 1e3)
 
     # ---- end to end through the reference-facing API: host frames in, host masks out, every step
-    batched = [{"image": [f for f in clip], "height": H, "width": W, "file_names": [f"f{i}" for i in range(T)]}]
+    clip_pin = clip.pin_memory()                     # "host→device copy of that step's inputs from pinned host memory"
+    batched = [{"image": [f for f in clip_pin], "height": H, "width": W, "file_names": [f"f{i}" for i in range(T)]}]
     for _ in range(max(3, args.warmup)):
         model(batched)
     barrier()

@@ -83,10 +83,7 @@ class SeqFormer(nn.Module):
         if self.clip_matching:
             return self._forward_clip_matching(frames, ori)
         run = self.runner(T, H, W, ori)
-        stage = run.frames_pin
-        for i, f in enumerate(frames):              # uint8-valued frames (float or uint8 tensors) -> pinned staging
-            stage[i].copy_(f)
-        scores, masks = run.run_host()
+        scores, masks = run.run_host(frames_list=frames)
         return SeqFormerEngine.finish_video(scores, masks, ori, self.apply_cls_thres, self.is_multi_cls)
 
 
