@@ -70,6 +70,12 @@ def test_graph_runner_and_meta_arch_output():
     other = model([{"image": synthetic_clip(T, H, W, seed + 7), "height": H, "width": W, "file_names": ["a", "b", "c"]}])
     assert all(torch.equal(a, b) for a, b in zip(got["pred_masks"], snapshot))
     assert other["pred_masks"][0].data_ptr() != got["pred_masks"][0].data_ptr()
+    # stream(): same results, in order, with two clips in flight
+    b2 = [{"image": synthetic_clip(T, H, W, seed + 7), "height": H, "width": W, "file_names": ["a", "b", "c"]}]
+    outs = list(model.stream([batched, b2, batched]))
+    assert len(outs) == 3 and outs[0]["pred_labels"] == got["pred_labels"] == outs[2]["pred_labels"]
+    assert all(torch.equal(a, b) for a, b in zip(outs[0]["pred_masks"], got["pred_masks"]))
+    assert all(torch.equal(a, b) for a, b in zip(outs[1]["pred_masks"], other["pred_masks"]))
     with pytest.raises(KeyError):
         SeqFormer(state_dict={k: v for k, v in sd.items() if "query_embed" not in k}, device="cuda")
 

@@ -64,11 +64,40 @@ class SeqFormer(nn.Module):
                                       precision=self.precision, swin=self.swin)
         self._runners = {}
 
-    def runner(self, T, H, W, ori_size):
-        key = (T, H, W, tuple(ori_size))
+    def runner(self, T, H, W, ori_size, slot=0):
+        key = (T, H, W, tuple(ori_size), slot)
         if key not in self._runners:
             self._runners[key] = ClipRunner(self.engine, T, H, W, ori_size)
         return self._runners[key]
+
+    def stream(self, videos, depth=2):
+        """Throughput-oriented evaluation: `for out in model.stream(iterable_of_batched_inputs)` yields exactly what
+        `model(batched_inputs)` returns, in order, while `depth` clips are in flight on alternating runners (own CUDA
+        graph, stream and pinned buffers each): clip i+1's staging / H2D / compute overlaps clip i's D2H and host-side
+        list building.  Same results as the synchronous call; whole-video (non clip-matching) inference only."""
+        if self.training or self.clip_matching:
+            raise NotImplementedError("stream() serves whole-video eval inference")
+        if self.engine is None:
+            raise RuntimeError("no weights loaded: call load_reference_state_dict(checkpoint['model'])")
+        from collections import deque
+        pending = deque()
+
+        def finish():
+            run, ori = pending.popleft()
+            scores, masks = run.collect()
+            return SeqFormerEngine.finish_video(scores, masks, ori, self.apply_cls_thres, self.is_multi_cls)
+        for n, batched_inputs in enumerate(videos):
+            video = batched_inputs[0]
+            frames = video["image"]
+            H, W = frames[0].shape[-2:]
+            ori = (video.get("height", H), video.get("width", W))
+            if len(pending) == depth:
+                yield finish()
+            run = self.runner(len(frames), H, W, ori, slot=n % depth)
+            run.submit(frames_list=frames)
+            pending.append((run, ori))
+        while pending:
+            yield finish()
 
     def forward(self, batched_inputs):
         if self.training:

@@ -49,6 +49,11 @@ class ClipRunner:
         goes through the staging buffer.  The outputs are FRESH pinned tensors every call (PyTorch's caching host
         allocator recycles a block only after the caller dropped it), so results of earlier clips are never
         overwritten — the reference returns new tensors too."""
+        self.submit(frames_u8, frames_list)
+        return self.collect()
+
+    def submit(self, frames_u8=None, frames_list=None):
+        """Stage the frames and enqueue H2D + graph + D2H on this runner's stream without waiting (see collect())."""
         if frames_list is not None:
             for i, f in enumerate(frames_list):
                 self.frames_pin[i].copy_(f)
@@ -61,5 +66,10 @@ class ClipRunner:
             self.run_device()
             scores_pin.copy_(self.scores, non_blocking=True)
             masks_pin.copy_(self.masks, non_blocking=True)
+        self._pending = (scores_pin, masks_pin)
+
+    def collect(self):
+        """Wait for the clip enqueued by submit() and return its (scores, masks) pinned host tensors."""
         self.stream.synchronize()
-        return scores_pin, masks_pin
+        out, self._pending = self._pending, None
+        return out
