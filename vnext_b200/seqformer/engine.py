@@ -216,8 +216,6 @@ class SeqFormerEngine:
             plan.extra["enc_posproj"] = [F.linear(plan.pos_flat[0], w["attn"]["oa_w"], w["attn"]["oa_b"]).contiguous()
                                          for w in self.enc]
             torch.backends.cuda.matmul.allow_tf32 = prev
-        if self.native:
-            plan.extra["gn_ws"] = torch.empty(2 * T * 32, dtype=torch.float32, device=dev)
         self._plans[key] = plan
         return plan
 
@@ -357,7 +355,9 @@ class SeqFormerEngine:
                 y = F.conv2d(feats[name].permute(0, 3, 1, 2), w, b, stride=2, padding=1).permute(0, 2, 3, 1)
                 y = y.reshape(T, h * wd, self.C)
             s0 = plan.extra["lsi_list"][l]
-            fused.groupnorm_nhwc(y, gw, gb, 32, 1e-5, out=X[:, s0:s0 + h * wd, :], stats_ws=plan.extra["gn_ws"])
+            # stats workspace per call (graph-private when captured): a per-plan one would be shared — and raced on —
+            # by the two runners that SeqFormer.stream() keeps in flight
+            fused.groupnorm_nhwc(y, gw, gb, 32, 1e-5, out=X[:, s0:s0 + h * wd, :])
         return X
 
     def backbone(self, x):
