@@ -147,7 +147,7 @@ class IDOLTrainModel(nn.Module):
         if self.tc:                                   # weight-gradient GEMMs (cuBLAS) in TF32 as well; process-global flag
             torch.backends.cuda.matmul.allow_tf32 = True
         self.device = torch.device(device)
-        spec = idol_r50_state_spec(num_queries, num_classes)
+        spec = self._state_spec(num_queries, num_classes)
         missing = [k for k in spec if k not in state_dict]
         if missing:
             raise KeyError(f"checkpoint is missing {len(missing)} keys, e.g. {missing[:3]}")
@@ -174,6 +174,10 @@ class IDOLTrainModel(nn.Module):
         self.criterion_b = critb.BatchedCriterion(num_classes, mask_out_stride=mask_stride)
         self.enc_layers = 1 + max(int(k.split(".")[5]) for k in spec if k.startswith(TR + "encoder.layers."))
         self.dec_layers = 1 + max(int(k.split(".")[5]) for k in spec if k.startswith(TR + "decoder.layers."))
+
+    @staticmethod
+    def _state_spec(num_queries, num_classes):
+        return idol_r50_state_spec(num_queries, num_classes)
 
     # ------------------------------------------------------------------ state dict in the reference's layout
     def reference_state_dict(self):
@@ -285,10 +289,13 @@ class IDOLTrainModel(nn.Module):
         return self._linear(o.transpose(1, 2).reshape(B, Lq, C), self.P[p + ".out_proj.weight"], self.P[p + ".out_proj.bias"])
 
     # ------------------------------------------------------------------ dense forward over all frames
-    def dense(self, frames):
-        """frames: [N,3,H,W] tensor or list of N [3,h_i,w_i] tensors, float/uint8 0..255 (N = 2 x videos: key, ref,
-        key, ref ...); ragged sizes are zero-padded after normalisation like ImageList.from_tensors(…, 32)
-        (idol.py:487-497).  -> dict(hs, coords, level_ref, last_ref, memory [N,S,C], shapes, lsi, sizes [(h,w)]*N)"""
+    def front(self, frames, level3_from_full_mask=False, frames_per_video=1):
+        """Normalise + pad + backbone + input_proj + token flattening + encoder geometry.  frames: [N,3,H,W] tensor or
+        list of N [3,h_i,w_i] tensors, float/uint8 0..255; ragged sizes are zero-padded after normalisation like
+        ImageList.from_tensors(…, 32) (idol.py:487-497).  `frames_per_video` > 1: valid ratios come from each video's
+        first frame (SeqFormer, deformable_transformer.py:107); `level3_from_full_mask`: the stride-64 level's padding
+        mask is resized from the full-resolution mask (SeqFormer segm:117) instead of from level 0's (IDOL segm:117-118).
+        -> dict(src, pos, pad [N,S,(C)], shapes, lsi, vr [N,L,2], enc_ref [N,S,L,2], sizes)"""
         if torch.is_tensor(frames):
             frames = list(frames)
         N = len(frames)
@@ -312,7 +319,8 @@ class IDOLTrainModel(nn.Module):
             s = F.group_norm(s, 32, self.P[f"{DETR}input_proj.{l}.1.weight"], self.P[f"{DETR}input_proj.{l}.1.bias"], 1e-5)
             with torch.no_grad():
                 # level masks: nearest-resized padding mask; level 3 resizes masks[0] (segm:117-118)
-                m = F.interpolate((mask if l < 3 else masks[0])[None].float(), size=s.shape[-2:]).to(torch.bool)[0]
+                base = mask if (l < 3 or level3_from_full_mask) else masks[0]
+                m = F.interpolate(base[None].float(), size=s.shape[-2:]).to(torch.bool)[0]
                 pos = self._sine_pos(m).flatten(1, 2)
             srcs.append(s.permute(0, 2, 3, 1).flatten(1, 2))                       # a view when s is channels-last
             masks.append(m)
@@ -325,6 +333,8 @@ class IDOLTrainModel(nn.Module):
         with torch.no_grad():
             vr = torch.stack([torch.stack([(~m[:, 0, :]).sum(1).float() / m.shape[2],
                                            (~m[:, :, 0]).sum(1).float() / m.shape[1]], -1) for m in masks], 1)   # [N,L,2]
+            if frames_per_video > 1:
+                vr = vr[0::frames_per_video].repeat_interleave(frames_per_video, 0)
             refs = []
             for l, (h, w) in enumerate(shapes.tolist()):
                 ry, rx = torch.meshgrid(torch.linspace(0.5, h - 0.5, h, device=self.device),
@@ -332,14 +342,26 @@ class IDOLTrainModel(nn.Module):
                 refs.append(torch.stack((rx.reshape(-1)[None] / (vr[:, None, l, 0] * w),
                                          ry.reshape(-1)[None] / (vr[:, None, l, 1] * h)), -1))
             enc_ref = torch.cat(refs, 1)[:, :, None] * vr[:, None]                               # [N,S,L,2]
-        out = src
+        return {"src": src, "pos": pos, "pad": pad, "shapes": shapes, "lsi": lsi, "vr": vr, "enc_ref": enc_ref,
+                "sizes": sizes}
+
+    def encode(self, fr):
+        out, pos, shapes, lsi, pad = fr["src"], fr["pos"], fr["shapes"], fr["lsi"], fr["pad"]
         for i in range(self.enc_layers):
             p = f"{TR}encoder.layers.{i}"
-            a = self._msda(p + ".self_attn", out + pos, enc_ref, out, shapes, lsi, pad)
+            a = self._msda(p + ".self_attn", out + pos, fr["enc_ref"], out, shapes, lsi, pad)
             out = self._ln(p + ".norm1", out + self._drop(a))
             f = self._lin(p + ".linear2", self._drop(self._lin(p + ".linear1", out, relu=True)))
             out = self._ln(p + ".norm2", out + self._drop(f))
-        memory = out
+        return out
+
+    def dense(self, frames):
+        """frames (N = 2 x videos: key, ref, key, ref ...) -> dict(hs, coords, level_ref, last_ref, memory [N,S,C],
+        shapes, lsi, sizes [(h,w)]*N)"""
+        fr = self.front(frames)
+        memory = self.encode(fr)
+        N = memory.shape[0]
+        shapes, lsi, pad, vr, sizes = fr["shapes"], fr["lsi"], fr["pad"], fr["vr"], fr["sizes"]
 
         qe = self.P[DETR + "query_embed.weight"]
         C = memory.shape[-1]

@@ -39,6 +39,10 @@ class SeqFormer(nn.Module):
             self.swin = dict(embed_dim=g("MODEL.SWIN.EMBED_DIM", 96), depths=tuple(g("MODEL.SWIN.DEPTHS", (2, 2, 6, 2))),
                              num_heads=tuple(g("MODEL.SWIN.NUM_HEADS", (3, 6, 12, 24))),
                              window_size=g("MODEL.SWIN.WINDOW_SIZE", 7))
+        self._cfg_get = g
+        self.dropout = None                     # None: cfg.MODEL.SeqFormer.DROPOUT (0.1)
+        self._state_dict = None
+        self._train_model = None
         self.__dict__.update(overrides)
         self.engine = None
         self._runners = {}
@@ -50,6 +54,7 @@ class SeqFormer(nn.Module):
 
     def load_reference_state_dict(self, state_dict):
         """Takes a reference-layout checkpoint (`model` dict of a DetectionCheckpointer .pth)."""
+        self._state_dict, self._train_model = state_dict, None
         spec = self.expected_state_spec()
         missing = [k for k in spec if k not in state_dict]
         if missing:
@@ -99,9 +104,52 @@ class SeqFormer(nn.Module):
         while pending:
             yield finish()
 
+    # ------------------------------------------------------------------ training (seqformer.py:217-225, :266-305)
+    def train_model(self, num_frames):
+        """The differentiable dense path (vnext_b200/seqformer/train.py), created on first use from the loaded weights."""
+        if self._train_model is None or self._train_model.nf != num_frames:
+            if self._state_dict is None:
+                raise RuntimeError("no weights loaded: call load_reference_state_dict(checkpoint['model'])")
+            if self.swin is not None:
+                raise NotImplementedError("the training path is built for the ResNet-50 backbone; Swin training needs the "
+                                          "window-attention backward, not built this round")
+            from .criterion import default_weight_dict
+            from .train import SeqFormerTrainModel
+            g = self._cfg_get
+            wd = default_weight_dict(g("MODEL.SeqFormer.CLASS_WEIGHT", 2.0), g("MODEL.SeqFormer.L1_WEIGHT", 5.0),
+                                     g("MODEL.SeqFormer.GIOU_WEIGHT", 2.0), g("MODEL.SeqFormer.MASK_WEIGHT", 2.0),
+                                     g("MODEL.SeqFormer.DICE_WEIGHT", 5.0), g("MODEL.SeqFormer.DEC_LAYERS", 6),
+                                     g("MODEL.SeqFormer.DEEP_SUPERVISION", True))
+            self._train_model = SeqFormerTrainModel(
+                self._state_dict, num_frames, device=self.device_name, num_classes=self.num_classes,
+                num_queries=self.num_queries, dropout=g("MODEL.SeqFormer.DROPOUT", 0.1) if self.dropout is None else self.dropout,
+                pixel_mean=self.pixel_mean, pixel_std=self.pixel_std, mask_stride=self.mask_stride, weight_dict=wd)
+        return self._train_model
+
+    def prepare_targets(self, batched_inputs):
+        """Per video: `Instances`-like objects of its frames -> {"labels","boxes" [n,nf,4],"masks" [n,nf,H,W],"size"}
+        (seqformer.py:266-305: an instance's label is the max over frames of class x valid)."""
+        from ..idol.criterion import xyxy_to_cxcywh
+        dev = self.device_name
+        out = []
+        for video in batched_inputs:
+            boxes, masks, classes = [], [], []
+            for t in video["instances"]:
+                h, w = t.image_size
+                b = t.gt_boxes.tensor.to(dev) / torch.as_tensor([w, h, w, h], dtype=torch.float, device=dev)
+                boxes.append(xyxy_to_cxcywh(b))
+                masks.append(t.gt_masks.tensor.to(dev))
+                classes.append(t.gt_classes.to(dev) * (t.gt_ids.to(dev) != -1))
+            out.append({"labels": torch.stack(classes, 0).max(0)[0], "boxes": torch.stack(boxes, 1),
+                        "masks": torch.stack(masks, 1), "size": torch.as_tensor([h, w], dtype=torch.long, device=dev)})
+        return out
+
     def forward(self, batched_inputs):
         if self.training:
-            raise NotImplementedError("vnext_b200 SeqFormer: the training step is not on this round's hot path")
+            frames = [f for video in batched_inputs for f in video["image"]]
+            model = self.train_model(len(batched_inputs[0]["image"])).train()
+            loss_dict, _ = model(frames, self.prepare_targets(batched_inputs))
+            return model.weighted(loss_dict)
         if self.engine is None:
             raise RuntimeError("no weights loaded: call load_reference_state_dict(checkpoint['model'])")
         video = batched_inputs[0]

@@ -226,6 +226,36 @@ def synthetic_clip_outputs(video_length=9, clip_length=5, stride=1, num_queries=
     return out
 
 
+def synthetic_clip_targets(num_videos, num_frames, height, width, seed=0, insts=3, num_classes=40):
+    """Clip-level ground truth in the format SeqFormer.prepare_targets produces (projects/SeqFormer/seqformer/
+    seqformer.py:266-305): per video {"labels" [n], "boxes" [n, nf, 4] (cx,cy,w,h normalised), "masks" [n, nf, H, W]
+    bool, "size" tensor([H, W])}: rectangles drifting over the frames."""
+    g = _gen("clip_targets", seed)
+    out = []
+    for v in range(num_videos):
+        labels = torch.randint(0, num_classes, (insts,), generator=g)
+        cx = torch.rand(insts, generator=g) * 0.5 + 0.25
+        cy = torch.rand(insts, generator=g) * 0.5 + 0.25
+        bw = torch.rand(insts, generator=g) * 0.25 + 0.1
+        bh = torch.rand(insts, generator=g) * 0.25 + 0.1
+        shift = (torch.rand(insts, 2, generator=g) - 0.5) * 0.08
+        boxes, masks = [], []
+        ys = torch.arange(height).view(1, height, 1)
+        xs = torch.arange(width).view(1, 1, width)
+        for f in range(num_frames):
+            x0 = ((cx + f * shift[:, 0] - bw / 2).clamp(0, 1) * width).round()
+            x1 = ((cx + f * shift[:, 0] + bw / 2).clamp(0, 1) * width).round()
+            y0 = ((cy + f * shift[:, 1] - bh / 2).clamp(0, 1) * height).round()
+            y1 = ((cy + f * shift[:, 1] + bh / 2).clamp(0, 1) * height).round()
+            masks.append((xs >= x0.view(-1, 1, 1)) & (xs < x1.view(-1, 1, 1)) & (ys >= y0.view(-1, 1, 1)) &
+                         (ys < y1.view(-1, 1, 1)))
+            boxes.append(torch.stack([(x0 + x1) / 2 / width, (y0 + y1) / 2 / height, (x1 - x0) / width,
+                                      (y1 - y0) / height], -1))
+        out.append({"labels": labels, "boxes": torch.stack(boxes, 1), "masks": torch.stack(masks, 1),
+                    "size": torch.as_tensor([height, width], dtype=torch.long)})
+    return out
+
+
 def make_msda_inputs(N, Lq, M, D, shapes, P, seed, dtype=torch.float32, loc_range=(0.0, 1.0)):
     """MSDA input recipe of the reference test (projects/IDOL/idol/models/ops/test.py:33-36):
     value ~ U(0, .01), sampling locations ~ U(loc_range), attention weights normalised over (L, P)."""
