@@ -96,3 +96,39 @@ def test_flat_gradient_allreduce_world2():
     # layout: backbone group first (its own learning rate), 64-element aligned segments
     assert groups[0][0] == 0 and groups[0][1] == groups[1][0] == 64 and groups[1][1] == 192
     assert offs["detr.detr.backbone.0.backbone.res3.0.conv1.weight"] == 0 and all(o % 64 == 0 for o in offs.values())
+
+
+def _numboxes_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vnext_b200.seqformer import criterion as crit
+    c = crit.SetCriterion(5, crit.default_weight_dict(), 2, world_size_fn=dist.get_world_size,
+                          all_reduce_fn=lambda t: dist.all_reduce(t))
+    g = torch.Generator().manual_seed(7)                       # identical predictions on both ranks ...
+    out = {"pred_logits": torch.randn(1, 6, 5, generator=g), "pred_boxes": torch.rand(1, 2, 6, 4, generator=g) * 0.5 + 0.2}
+    n = 1 + 2 * rank                                           # ... but rank 0 has 1 ground truth, rank 1 has 3
+    tg = [{"labels": torch.arange(n) % 5, "boxes": torch.rand(n, 2, 4, generator=g) * 0.4 + 0.3,
+           "masks": torch.zeros(n, 2, 32, 32, dtype=torch.bool), "size": torch.tensor([32, 32])}]
+    ind = c.matcher(out, tg)
+    out["pred_masks"] = [torch.zeros(1, n, 2, 8, 8)]
+    losses = c(out, tg, [ind])
+    alone = crit.SetCriterion(5, crit.default_weight_dict(), 2)(out, tg, [ind])
+    q.put((rank, float(losses["loss_bbox"]), float(alone["loss_bbox"]), n))
+    dist.destroy_process_group()
+
+
+def test_seqformer_num_boxes_is_the_cross_rank_mean_world2():
+    """SeqFormer normalises every loss by the MEAN ground-truth count over ranks (deformable_detr.py:415-420)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_numboxes_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, dist_loss, solo_loss, n in res:
+        assert abs(dist_loss - solo_loss * n / 2.0) < 1e-6 * max(1.0, abs(solo_loss))       # mean count = (1 + 3) / 2
