@@ -25,7 +25,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {"720p": (5, 720, 1280), "480p": (5, 480, 864), "swinl_720p": (5, 720, 1280),
-             "idol_train": (8, 480, 864)}          # BASELINE configs[2]: 4 videos x (key, ref) frames per GPU
+             "idol_train": (8, 480, 864),          # BASELINE configs[2]: 4 videos x (key, ref) frames per GPU
+             "seqformer_train": (10, 480, 864)}    # 2 clips x 5 frames per GPU (INPUT.SAMPLING_FRAME_NUM: 5)
 METRIC = "frames/sec SeqFormer-R50 T=5 720p synthetic"
 
 
@@ -136,6 +137,10 @@ def reference_arm(args, rank, world):
     if rank != 0:
         return
     T, H, W = WORKLOADS[args.workload]
+    if args.workload == "seqformer_train":
+        print(json.dumps({"impl": "reference", "unavailable": "no CPU leg for the optional seqformer_train workload; "
+                          "use --workload idol_train (BASELINE configs[2]) or the default inference workload"}), flush=True)
+        return
     if args.workload == "idol_train":
         threads = min(32, os.cpu_count() or 1)
         t0 = time.perf_counter()
@@ -396,14 +401,25 @@ def train_arm(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    NF, H, W = WORKLOADS["idol_train"]
-    model = T.IDOLTrainModel(fill_state_dict(idol_r50_state_spec(), 0), device=dev, dropout=0.1,
-                             precision=args.precision).train()
-    trainer = T.IDOLTrainer(model)
+    seq = args.workload == "seqformer_train"
+    NF, H, W = WORKLOADS[args.workload]
     host = torch.stack(synthetic_clip(NF, H, W, rank)).to(torch.uint8).pin_memory()
-    det, ref = synthetic_targets(NF // 2, H, W, rank)
-    det = [{k: v.to(dev) for k, v in t.items()} for t in det]
-    ref = [{k: v.to(dev) for k, v in t.items()} for t in ref]
+    if seq:
+        from vnext_b200.seqformer import train as ST
+        from vnext_b200.seqformer.state_spec import seqformer_r50_state_spec
+        from vnext_b200.synth import synthetic_clip_targets
+        model = ST.SeqFormerTrainModel(fill_state_dict(seqformer_r50_state_spec(), 0), 5, device=dev, dropout=0.1,
+                                       precision=args.precision).train()
+        trainer = ST.SeqFormerTrainer(model)
+        tg = [{k: v.to(dev) for k, v in t.items()} for t in synthetic_clip_targets(NF // 5, 5, H, W, rank)]
+        step_args = (tg,)
+    else:
+        model = T.IDOLTrainModel(fill_state_dict(idol_r50_state_spec(), 0), device=dev, dropout=0.1,
+                                 precision=args.precision).train()
+        trainer = T.IDOLTrainer(model)
+        det, ref = synthetic_targets(NF // 2, H, W, rank)
+        step_args = ([{k: v.to(dev) for k, v in t.items()} for t in det],
+                     [{k: v.to(dev) for k, v in t.items()} for t in ref])
     frames = host.to(dev).float()
     random.seed(rank)
 
@@ -412,7 +428,7 @@ def train_arm(args, rank, world, local_rank):
             dist.barrier()
 
     for _ in range(max(3, args.warmup)):
-        trainer.step(frames, det, ref)
+        trainer.step(frames, *step_args)
     sampler = ClockSampler(local_rank)
     barrier()
     torch.cuda.synchronize()
@@ -421,7 +437,7 @@ def train_arm(args, rank, world, local_rank):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        trainer.step(frames, det, ref)
+        trainer.step(frames, *step_args)
     ev1.record()
     torch.cuda.synchronize()
     launches = _cabi.lib().vnext_launch_count() - n0
@@ -435,13 +451,13 @@ def train_arm(args, rank, world, local_rank):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _, total, _ = trainer.step(host.to(dev, non_blocking=True).float(), det, ref)
+        _, total, _ = trainer.step(host.to(dev, non_blocking=True).float(), *step_args)
         total.item()
     torch.cuda.synchronize()
     e2e = world * args.steps * NF / (max_over_ranks((time.perf_counter() - t0) * 1e3, dev) / 1e3)
 
     with _cabi.KernelTimer() as kt:
-        trainer.step(frames, det, ref)
+        trainer.step(frames, *step_args)
     agg = kt.summary()
     hbm_peak, _, peak_src = load_peaks()
     kern = {k: {"calls": v["calls"], "us_per_step": round(v["us"], 1),
@@ -450,23 +466,26 @@ def train_arm(args, rank, world, local_rank):
     roof = None
     if dom:
         ach = dom["bytes"] / (dom["us"] * 1e-6) / 1e9
-        roof = {"bound": "hbm", "kernel": "msda_bwd_tile_kernel (encoder shape, 8 frames)", "achieved": round(ach, 1),
+        roof = {"bound": "hbm", "kernel": f"msda_bwd_tile_kernel (encoder shape, {NF} frames)", "achieved": round(ach, 1),
                 "peak": hbm_peak, "unit": "GB/s", "frac": round(ach / hbm_peak, 4), "traffic": None,
                 "peak_source": peak_src, "own_kernels": kern}
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not seq:
         threads = min(32, os.cpu_count() or 1)
         cpu = {"value": round(cpu_train_sample(H, W, threads), 4), "unit": "frames/s", "cores": threads, "kind": "port",
                "sample": "1 (key, ref) pair 480x864, forward+backward once (no optimiser), oracle MSDA on host threads"}
     if rank == 0:
         print(json.dumps({
-            "metric": TRAIN_METRIC, "value": round(fps, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "metric": TRAIN_METRIC.replace("IDOL-R50 two-frame", "SeqFormer-R50 five-frame clip") if seq else TRAIN_METRIC,
+            "value": round(fps, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "tf32 GEMMs/convs, f32 MSDA + accumulate" if args.precision == "tf32" else "f32 (cuDNN default TF32 convs)",
             "data": "synthetic",
-            "config": {"workload": f"IDOL-R50 training step, {NF // 2} videos x (key, ref) frames {H}x{W} per GPU, 300 "
-                                   "queries, dropout 0.1, simOTA + 7 loss terms x 6 levels, AdamW lr 1e-4 (backbone x0.1), "
-                                   "clip 0.01; activations >> L2 so no flush", "parallelism": f"dp{world}"},
+            "config": {"workload": (f"SeqFormer-R50 training step, {NF // 5} clips x 5 frames {H}x{W} per GPU, 300 queries, "
+                                    "dropout 0.1, Hungarian + 5 loss terms x 6 levels, AdamW, clip 0.01" if seq else
+                                    f"IDOL-R50 training step, {NF // 2} videos x (key, ref) frames {H}x{W} per GPU, 300 "
+                                    "queries, dropout 0.1, simOTA + 7 loss terms x 6 levels, AdamW lr 1e-4 (backbone x0.1), "
+                                    "clip 0.01") + "; activations >> L2 so no flush", "parallelism": f"dp{world}"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int(host.numel()),
                     "d2h_bytes_per_step": 4},
@@ -495,7 +514,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        (train_arm if args.workload == "idol_train" else own_arm)(args, rank, world, local_rank)
+        (train_arm if args.workload.endswith("_train") else own_arm)(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist
