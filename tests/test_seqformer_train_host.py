@@ -53,10 +53,10 @@ def compare(model, gold, loss_dict, outputs, indices_of, rtol_loss, rtol_norm, t
     return worst
 
 
-def run(device, rtol_loss, rtol_norm, tol_grad, precision="fp32"):
+def run(device, rtol_loss, rtol_norm, tol_grad, precision="fp32", batched=False):
     gold = dict(np.load(GOLD))
     sd = fill_state_dict(seqformer_r50_state_spec(), SEED)
-    model = ST.SeqFormerTrainModel(sd, NF, device=device, dropout=0.0, precision=precision).train()
+    model = ST.SeqFormerTrainModel(sd, NF, device=device, dropout=0.0, precision=precision, batched=batched).train()
     frames = torch.stack(synthetic_clip(B * NF, H, W, SEED)).to(device)
     targets = [{k: v.to(device) for k, v in t.items()} for t in synthetic_clip_targets(B, NF, H, W, SEED)]
     seen = []
@@ -66,13 +66,15 @@ def run(device, rtol_loss, rtol_norm, tol_grad, precision="fp32"):
     total = sum(model.weighted(loss_dict).values())
     np.testing.assert_allclose(float(total.detach()), float(gold["total"]), rtol=rtol_loss)
     total.backward()
-    return compare(model, gold, loss_dict, outputs, lambda lvl: seen[lvl], rtol_loss, rtol_norm, tol_grad), model
+    indices_of = (lambda lvl: outputs["indices_list"][lvl]) if batched else (lambda lvl: seen[lvl])
+    return compare(model, gold, loss_dict, outputs, indices_of, rtol_loss, rtol_norm, tol_grad), model
 
 
 @pytest.mark.timeout(900)
-def test_train_forward_backward_matches_reference(monkeypatch):
+@pytest.mark.parametrize("batched", [False, True])
+def test_train_forward_backward_matches_reference(monkeypatch, batched):
     monkeypatch.setattr(IT, "MSDeformAttnFunction", OracleMSDA)
-    worst, model = run("cpu", 1e-4, 2e-3, 2e-3)
+    worst, model = run("cpu", 1e-4, 2e-3, 2e-3, batched=batched)
     print("worst grad-norm rel err", worst)
     # encoder layers carry an `output_proj_box` the encode path never uses (ms_deform_attn.py:89-124): zero gradient
     unused = [k for k, p in model.flat.params.items() if float(p.grad.abs().sum()) == 0]

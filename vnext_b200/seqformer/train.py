@@ -107,6 +107,102 @@ class SeqFormerTrainModel(IDOLTrainModel):
     def forward(self, frames, targets):
         """-> (loss_dict unweighted, outputs).  frames: B*nf frames video-major ([B*nf,3,H,W] or a list); targets:
         per video {"labels","boxes" [n,nf,4],"masks" [n,nf,H,W],"size"} as SeqFormer.prepare_targets builds them."""
+        if self.batched:
+            return self.forward_batched(frames, targets)
+        return self.forward_sequential(frames, targets)
+
+    def forward_batched(self, frames, targets):
+        """All six decoder levels at once: one cost tensor and ONE device→host copy for the 6 x B Hungarian problems,
+        every loss a dense / indexed reduction over [levels, clips, queries], every matched (level, clip, query) through
+        the dynamic mask head in one batch per frame.  Same goldens as forward_sequential (tests/test_seqformer_train_
+        host.py); opt-in (`batched=True`) until it has been timed on the hardware."""
+        from scipy.optimize import linear_sum_assignment
+        from ..idol.criterion import cxcywh_to_xyxy, paired_giou_loss, pairwise_giou, pad_masks
+        from ..idol.criterion_batched import focal_sum
+        d = self.dense(frames)
+        nf, L, dev = self.nf, self.dec_layers, self.device
+        hs = torch.stack(d["hs"])                                                       # [L,B,nq,C]
+        B, nq = hs.shape[1:3]
+        wc = torch.stack([self.P[f"{DETR}class_embed.{i}.weight"] for i in range(L)])
+        bc = torch.stack([self.P[f"{DETR}class_embed.{i}.bias"] for i in range(L)])
+        logits = torch.baddbmm(bc[:, None], hs.flatten(1, 2), wc.transpose(1, 2)).view(L, B, nq, -1)
+        boxes = torch.stack(d["coords"])                                                # [L,B,nf,nq,4]
+        K = logits.shape[-1]
+        sizes = [len(t["labels"]) for t in targets]
+        n_tot = sum(sizes)
+        tgt_ids = torch.cat([t["labels"] for t in targets])
+        tgt_box = torch.cat([t["boxes"] for t in targets]).reshape(n_tot, nf, 4)
+        with torch.no_grad():                                                           # models/matcher.py:53-91, all levels
+            prob = logits.flatten(0, 2).sigmoid()
+            ob = boxes.permute(0, 1, 3, 2, 4).flatten(0, 2)                             # [L*B*nq, nf, 4]
+            c_bbox = torch.cdist(ob.flatten(1, 2), tgt_box.flatten(1, 2))
+            tb = torch.clip(tgt_box, min=1e-7, max=1)
+            c_giou = 0
+            for i in range(nf):
+                c_giou = c_giou - pairwise_giou(cxcywh_to_xyxy(ob[:, i]), cxcywh_to_xyxy(tb[:, i]))
+            c_giou = c_giou / nf
+            neg = 0.75 * (prob ** 2.0) * (-(1 - prob + 1e-8).log())
+            pos = 0.25 * ((1 - prob) ** 2.0) * (-(prob + 1e-8).log())
+            cc, cb, cg = self.criterion.costs
+            C = (cb * c_bbox + cc * (pos[:, tgt_ids] - neg[:, tgt_ids]) + cg * c_giou).view(L, B, nq, n_tot).cpu()
+        lv, bi, qi, ti, gi = [], [], [], [], []
+        off = 0
+        indices_list = [[None] * B for _ in range(L)]
+        for b, n in enumerate(sizes):
+            for l in range(L):
+                r, c = linear_sum_assignment(C[l, b][:, off:off + n])
+                indices_list[l][b] = (torch.as_tensor(r, dtype=torch.int64), torch.as_tensor(c, dtype=torch.int64))
+                lv += [l] * len(r); bi += [b] * len(r); qi += r.tolist(); ti += c.tolist(); gi += (c + off).tolist()
+            off += n
+        lv, bi, qi, ti, gi = (torch.tensor(x, dtype=torch.long, device=dev) for x in (lv, bi, qi, ti, gi))
+        nb = torch.as_tensor([float(n_tot)], device=dev)
+        if self.criterion.all_reduce_fn is not None:
+            self.criterion.all_reduce_fn(nb)
+        num_boxes = torch.clamp(nb / self.criterion.world_size_fn(), min=1)[0]
+        zero = torch.zeros(L, device=dev)
+        # labels
+        classes = torch.full((L, B, nq), K, dtype=torch.int64, device=dev)
+        classes[lv, bi, qi] = tgt_ids[gi]
+        onehot = F.one_hot(classes, K + 1)[..., :K].to(logits.dtype)
+        losses = {"loss_ce": focal_sum(logits, onehot, self.criterion.focal_alpha).flatten(1).sum(1) / num_boxes}
+        last = lv == L - 1
+        sel = logits[L - 1][bi[last], qi[last]]
+        want = tgt_ids[gi[last]]
+        class_error = 100 - ((sel.argmax(-1) == want).float().sum() * (100.0 / max(int(last.sum()), 1)))
+        # boxes
+        src = boxes.permute(0, 1, 3, 2, 4)[lv, bi, qi]                                   # [n, nf, 4]
+        tgt = tgt_box[gi]
+        l1 = (src - tgt).abs().flatten(1).sum(1) / nf
+        gl = paired_giou_loss(cxcywh_to_xyxy(src.flatten(0, 1)), cxcywh_to_xyxy(tgt.flatten(0, 1))).view(-1, nf).sum(1) / nf
+        losses["loss_bbox"] = zero.index_add(0, lv, l1) / num_boxes
+        losses["loss_giou"] = zero.index_add(0, lv, gl) / num_boxes
+        # masks: one dynamic-head batch per frame over all matched (level, clip, query) triples
+        params = self._mlp("detr.controller", hs[lv, bi, qi])
+        scale = torch.stack([torch.stack([t["size"][1], t["size"][0]]).to(dev, torch.float32) for t in targets])   # (w, h)
+        ref_px = torch.stack([inverse_sigmoid(r).sigmoid()[..., :2] for r in d["level_ref"]])                    # [L,B,nf,nq,2]
+        ml = []
+        for f in range(nf):
+            feat = self.mask_features(d["memory"][:, f], d["shapes"], d["lsi"])
+            ml.append(self.instance_masks_batched(feat, bi, ref_px[lv, bi, f, qi] * scale[bi], params))
+        ml = torch.stack(ml, 1)                                                          # [n, nf, h, w]
+        tm = pad_masks([t["masks"].flatten(0, 1) for t in targets]).to(ml)
+        s = self.criterion.mask_out_stride
+        tm = tm[:, :, int(s // 2)::s, int(s // 2)::s]
+        tm = tm.reshape(B, -1, nf, tm.shape[-2], tm.shape[-1])[bi, ti]
+        srcm, tgtm = ml.flatten(1), tm.flatten(1)
+        p = srcm.sigmoid()
+        dice = 1 - (2 * (p * tgtm).sum(1) + 1) / (p.sum(1) + tgtm.sum(1) + 1)
+        losses["loss_mask"] = zero.index_add(0, lv, focal_sum(srcm, tgtm).mean(1)) / num_boxes
+        losses["loss_dice"] = zero.index_add(0, lv, dice) / num_boxes
+        out = {"class_error": class_error}
+        for k, v in losses.items():
+            out[k] = v[L - 1]
+            for i in range(L - 1):
+                out[f"{k}_{i}"] = v[i]
+        return out, {"pred_logits": logits[-1], "pred_boxes": boxes[-1], "indices_list": indices_list}
+
+    def forward_sequential(self, frames, targets):
+        """The reference's control flow level by level (criterion.py) — the parity anchor for forward_batched."""
         d = self.dense(frames)
         nf = self.nf
         B = d["memory"].shape[0]
