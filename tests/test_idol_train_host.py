@@ -162,3 +162,25 @@ def test_prepare_targets_matches_reference_format():
     insts[0].gt_ids[1] = -1
     d3, r3 = m.prepare_targets(insts)
     assert len(d3[0]["labels"]) == len(r3[0]["labels"]) == 2 and len(d3[1]["labels"]) == 3
+
+
+def test_trainer_checkpoint_roundtrip():
+    """state_dict(): weights in the reference key layout + flat Adam moments + step; load_state_dict() restores them
+    into a freshly built model (resume)."""
+    spec = idol_r50_state_spec()
+    a = T.IDOLTrainer(T.IDOLTrainModel(fill_state_dict(spec, 1), device="cpu"))
+    with torch.no_grad():
+        a.flat.w.add_(0.01)                       # "trained" weights and non-trivial optimiser state
+        a.flat.m.uniform_(-1, 1)
+        a.flat.v.uniform_(0, 1)
+    a.step_count = 17
+    state = a.state_dict()
+    assert set(state["model"]) == set(spec) and state["step"] == 17
+    b = T.IDOLTrainer(T.IDOLTrainModel(fill_state_dict(spec, 2), device="cpu"))
+    b.load_state_dict(state)
+    assert all(torch.equal(a.flat.params[k], b.flat.params[k]) for k in a.flat.params)    # (alignment gaps are not state)
+    assert torch.equal(a.flat.m, b.flat.m) and torch.equal(a.flat.v, b.flat.v)
+    assert b.step_count == 17 and all(torch.equal(a.model.frozen[k], b.model.frozen[k]) for k in a.model.frozen)
+    state["layout"] = {}
+    with pytest.raises(ValueError, match="layout"):
+        b.load_state_dict(state)

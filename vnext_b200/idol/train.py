@@ -568,6 +568,28 @@ class IDOLTrainer:
         total.backward()
         return self.apply_gradients(), total.detach(), weighted
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self):
+        """Everything a resume needs: weights in the REFERENCE key layout (what DetectionCheckpointer writes under
+        "model"), the flat Adam moments with the layout they refer to, and the step count."""
+        return {"model": self.model.reference_state_dict(), "adam_m": self.flat.m.detach().cpu().clone(),
+                "adam_v": self.flat.v.detach().cpu().clone(), "step": self.step_count,
+                "layout": {k: v[:2] for k, v in self.flat.offsets.items()}}
+
+    def load_state_dict(self, state):
+        layout = {k: v[:2] for k, v in self.flat.offsets.items()}
+        if state["layout"] != layout:
+            raise ValueError("optimizer state was saved for a different parameter layout")
+        sd = state["model"]
+        with torch.no_grad():
+            for k, p in self.flat.params.items():
+                p.copy_(sd[k].to(p.device, p.dtype))
+            for k, t in self.model.frozen.items():
+                t.copy_(sd[k].to(t.device, t.dtype))
+            self.flat.m.copy_(state["adam_m"])
+            self.flat.v.copy_(state["adam_v"])
+        self.step_count = int(state["step"])
+
     def reduce_gradients(self):
         """Sum the flat gradient buffer over ranks (one collective) and set the device-side scale that turns it into
         the clipped mean gradient.  -> L2 norm of the mean gradient (a device scalar; nothing is synchronised)."""
