@@ -88,6 +88,26 @@ int vnext_msda_forward_fused(int dtype, const void *value, const int64_t *spatia
                              void *stream);
 
 /*
+ * Forward for SELF-attention over the pixel grid (the encoder shape: num_query == spatial_size, query i IS pixel i of
+ * the flattened pyramid — DeformableTransformerEncoderLayer, projects/IDOL/idol/models/deformable_transformer.py:
+ * 230-261).  Same result as vnext_msda_forward / vnext_msda_forward_fused for ANY sampling locations; it is faster
+ * when a query's samples fall near its own pixel, because each (query tile, head) stages a window of every level in
+ * shared memory with TMA box loads (zero fill outside the level = the reference's border rule) and gathers from
+ * there; samples that leave the window by more than `margin` pixels are fetched from global memory in the same loop.
+ *   spatial_shapes_host / level_start_index_host: HOST copies of the int64 tensors (the TMA descriptors are built from
+ *   them per call); levels must tile [0, spatial_size) in order.
+ *   Front-end: either (sampling_loc, attn_weight) as vnext_msda_forward, or — when offsets_logits != NULL — the fused
+ *   one of vnext_msda_forward_fused (offsets_logits, row_pitch, reference_points, ref_dim, ref_shared).
+ * Needs channels == 32, num_levels <= 4, num_levels*num_point in {8, 16, 32}, value fp32 or bf16 (16-byte aligned).
+ */
+int vnext_msda_forward_selfattn(int dtype, const void *value, const int64_t *spatial_shapes_host,
+                                const int64_t *level_start_index_host, const void *sampling_loc,
+                                const void *attn_weight, const float *offsets_logits, int row_pitch,
+                                const float *reference_points, int ref_dim, int ref_shared, int batch,
+                                int spatial_size, int num_heads, int channels, int num_levels, int num_point,
+                                int margin, void *output, void *stream);
+
+/*
  * Backward.  grad_output [batch, num_query, num_heads*channels] (dtype).
  * Outputs are fully (over)written: grad_value like value (zero-filled then accumulated with
  * atomics, as the reference), grad_sampling_loc like sampling_loc, grad_attn_weight like attn_weight.
@@ -161,13 +181,15 @@ int vnext_conv3x3_tf32(const float *x, const float *weight_khwc, const float *bi
  *   vnext_stem_pool     out = maxpool3x3/s2/p1(relu(x + bias))    — BasicStem tail (resnet.py:355-359); x [N,H,W,C]
  *   vnext_groupnorm_nhwc GroupNorm(groups, C == 8*groups) over x [N, HW, C], written to `out` with batch stride
  *                       `out_batch_stride` elements (lets the caller place a level directly inside the [T, S, C]
- *                       token tensor); stats_ws: 2*N*groups floats of scratch (deformable_detr.py:64-78)
+ *                       token tensor); stats_ws: vnext_groupnorm_workspace_floats(N, HW, groups) floats of scratch
+ *                       (deformable_detr.py:64-78).  Deterministic: per-CTA partial sums folded in a fixed order.
  *   vnext_preprocess    frames [T,3,H,W] (uint8 if in_is_u8 else fp32, 0..255) -> (x - mean)/std, zero padded to
  *                       [T,Hp,Wp,3] channels-last (seqformer.py:413-429, util/misc.py:288-316); mean3/std3: HOST.
  */
 int vnext_bias_act(const float *x, const float *bias, const float *residual, float *out, long long rows, int C,
                    int relu, void *stream);
 int vnext_stem_pool(const float *x, const float *bias, float *out, int N, int H, int W, int C, void *stream);
+size_t vnext_groupnorm_workspace_floats(int N, int HW, int groups);
 int vnext_groupnorm_nhwc(const float *x, const float *gamma, const float *beta, float *out,
                          long long out_batch_stride, float *stats_ws, int N, int HW, int C, int groups, float eps,
                          void *stream);

@@ -28,6 +28,7 @@ SIGNATURES = {
     "vnext_conv3x3_tf32": (_c_int, [_c_void_p] * 4 + [_c_int] * 6 + [_c_void_p]),
     "vnext_bias_act": (_c_int, [_c_void_p] * 4 + [ctypes.c_longlong, _c_int, _c_int, _c_void_p]),
     "vnext_stem_pool": (_c_int, [_c_void_p] * 3 + [_c_int] * 4 + [_c_void_p]),
+    "vnext_groupnorm_workspace_floats": (_c_size_t, [_c_int] * 3),
     "vnext_groupnorm_nhwc": (_c_int, [_c_void_p] * 4 + [ctypes.c_longlong, _c_void_p, _c_int, _c_int, _c_int, _c_int,
                                       ctypes.c_float, _c_void_p]),
     "vnext_preprocess": (_c_int, [_c_int, _c_void_p, _c_void_p] + [_c_int] * 5 + [_c_void_p, _c_void_p, _c_void_p]),

@@ -105,6 +105,27 @@ int vnext_msda_forward(int dtype, const void *value, const int64_t *spatial_shap
                                static_cast<cudaStream_t>(stream));
 }
 
+int vnext_msda_forward_selfattn(int dtype, const void *value, const int64_t *spatial_shapes_host,
+                                const int64_t *level_start_index_host, const void *sampling_loc, const void *attn_weight,
+                                const float *offsets_logits, int row_pitch, const float *reference_points, int ref_dim,
+                                int ref_shared, int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                                int num_point, int margin, void *output, void *stream) {
+    int rc = check_dims("vnext_msda_forward_selfattn", dtype, batch, spatial_size, num_heads, channels, num_levels,
+                        spatial_size, num_point);
+    if (rc) return rc;
+    const bool empty = (long long)batch * spatial_size == 0;
+    VNEXT_CHECK_ARG(empty || (value && spatial_shapes_host && level_start_index_host && output &&
+                              ((sampling_loc && attn_weight) || (offsets_logits && reference_points))),
+                    "vnext_msda_forward_selfattn: null tensor pointer");
+    VNEXT_CHECK_ARG(channels == 32 && msda_window_supported(dtype, channels, num_levels, num_point),
+                    "vnext_msda_forward_selfattn: needs channels == 32, num_levels <= 4, num_levels*num_point in {8,16,32}, "
+                    "fp32/bf16 value (got D=%d L=%d K=%d dtype=%d)", channels, num_levels, num_point, dtype);
+    return msda_forward_window_device(dtype, value, spatial_shapes_host, level_start_index_host,
+                                      static_cast<const float *>(sampling_loc), static_cast<const float *>(attn_weight),
+                                      offsets_logits, row_pitch, reference_points, ref_dim, ref_shared, batch, spatial_size,
+                                      num_heads, num_levels, num_point, margin, output, static_cast<cudaStream_t>(stream));
+}
+
 int vnext_msda_backward(int dtype, const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
                         const void *sampling_loc, const void *attn_weight, const void *grad_output, int batch,
                         int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point,

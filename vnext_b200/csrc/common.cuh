@@ -80,6 +80,22 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
         "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+// 4 consecutive channels to fp32 (16 B) or bf16 (8 B) storage
+__device__ __forceinline__ void store4(float *dst, const float4 &v) { *reinterpret_cast<float4 *>(dst) = v; }
+__device__ __forceinline__ void store4(__nv_bfloat16 *dst, const float4 &v) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t *>(&lo);
+    u.y = *reinterpret_cast<const uint32_t *>(&hi);
+    *reinterpret_cast<uint2 *>(dst) = u;
+}
+__device__ __forceinline__ float4 load4(const float *src) { return *reinterpret_cast<const float4 *>(src); }
+__device__ __forceinline__ float4 load4(const __nv_bfloat16 *src) {
+    const uint2 u = *reinterpret_cast<const uint2 *>(src);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
 // vectorised fp32 reduction to global memory (sm_90+): one RED for four channels.
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)

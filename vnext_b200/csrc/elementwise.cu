@@ -59,17 +59,21 @@ __global__ void __launch_bounds__(256) stem_pool_kernel(const float4 *__restrict
     }
 }
 
-// GroupNorm over [N, HW, C] (channels-last), G groups of C/G = 8 channels: statistics pass + apply pass.
-// stats[n][g] = (sum, sumsq) accumulated with one atomicAdd pair per (CTA, group).
+// GroupNorm over [N, HW, C] (channels-last), G groups of C/G = 8 channels: partial statistics -> fixed-order combine
+// -> apply.  Deterministic by construction (no atomics): every CTA of the statistics pass writes its own (sum, sumsq)
+// per group, and ONE thread per (n, group) folds them in block order with Chan's parallel-variance update in fp64, so the
+// result does not depend on CTA scheduling (two concurrent replays of one CUDA graph give identical bits) and the
+// variance does not suffer the E[x^2] - mean^2 cancellation over the whole level.
 constexpr int kGnThreads = 256;
-__global__ void __launch_bounds__(kGnThreads) groupnorm_stats_kernel(const float4 *__restrict__ x, float *stats, int HW,
-                                                                     int C, int rows_per_cta) {
+constexpr int kGnRowsPerCta = 64;
+__global__ void __launch_bounds__(kGnThreads) groupnorm_partial_kernel(const float4 *__restrict__ x, float *__restrict__ part,
+                                                                       int HW, int C) {
     // thread -> (row offset, float4 column); C/4 float4 columns, two per 8-channel group
     const int c4 = C / 4;
     const int n = blockIdx.y;
     const int col = threadIdx.x % c4, rsub = threadIdx.x / c4, rstep = kGnThreads / c4;
-    const int r0 = blockIdx.x * rows_per_cta;
-    const int r1 = min(HW, r0 + rows_per_cta);
+    const int r0 = blockIdx.x * kGnRowsPerCta;
+    const int r1 = min(HW, r0 + kGnRowsPerCta);
     float s = 0.f, ss = 0.f;
     for (int r = r0 + rsub; r < r1; r += rstep) {
         const float4 v = x[((long long)n * HW + r) * c4 + col];
@@ -88,33 +92,52 @@ __global__ void __launch_bounds__(kGnThreads) groupnorm_stats_kernel(const float
                 a += sh_s[k * c4 + 2 * threadIdx.x + h];
                 b += sh_ss[k * c4 + 2 * threadIdx.x + h];
             }
-        atomicAdd(stats + ((long long)n * G + threadIdx.x) * 2, a);
-        atomicAdd(stats + ((long long)n * G + threadIdx.x) * 2 + 1, b);
+        float *dst = part + (((long long)n * gridDim.x + blockIdx.x) * G + threadIdx.x) * 2;
+        dst[0] = a;
+        dst[1] = b;
     }
 }
 
+// stats[n][g] = (mean, rstd): blocks folded in index order, Chan et al. pairwise update in double precision.
+__global__ void groupnorm_combine_kernel(const float *__restrict__ part, float *__restrict__ stats, int nblk, int HW, int G,
+                                         float eps) {
+    const int n = blockIdx.x, g = threadIdx.x;
+    if (g >= G) return;
+    double cnt = 0.0, mean = 0.0, m2 = 0.0;
+    for (int b = 0; b < nblk; ++b) {
+        const float *p = part + (((long long)n * nblk + b) * G + g) * 2;
+        const double cb = 8.0 * (double)min(kGnRowsPerCta, HW - b * kGnRowsPerCta);
+        const double sb = (double)p[0], mb = sb / cb;
+        const double m2b = fmax((double)p[1] - sb * mb, 0.0);
+        const double tot = cnt + cb, delta = mb - mean;
+        m2 += m2b + delta * delta * cnt * cb / tot;
+        mean += delta * cb / tot;
+        cnt = tot;
+    }
+    stats[((long long)n * G + g) * 2] = (float)mean;
+    stats[((long long)n * G + g) * 2 + 1] = (float)(1.0 / sqrt(m2 / cnt + (double)eps));
+}
+
+template <typename OT>
 __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float4 *__restrict__ x, const float *__restrict__ stats,
                                                               const float4 *__restrict__ gamma, const float4 *__restrict__ beta,
-                                                              float4 *__restrict__ out, int N, int HW, int C,
-                                                              long long out_batch_stride4, float eps) {
+                                                              OT *__restrict__ out, int N, int HW, int C,
+                                                              long long out_batch_stride, float eps) {
     const int c4 = C / 4, G = C / 8;
     const long long per = (long long)HW * c4;
-    const float inv_cnt = 1.f / (8.f * HW);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per * N; i += (long long)gridDim.x * blockDim.x) {
         const int n = (int)(i / per);
         const long long j = i % per;
         const int col = (int)(j % c4);
         const float *st = stats + ((long long)n * G + col / 2) * 2;
-        const float mean = st[0] * inv_cnt;
-        const float var = fmaxf(st[1] * inv_cnt - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + eps);
+        const float mean = st[0], rstd = st[1];
         const float4 v = x[i], g = __ldg(gamma + col), b = __ldg(beta + col);
         float4 o;
         o.x = (v.x - mean) * rstd * g.x + b.x;
         o.y = (v.y - mean) * rstd * g.y + b.y;
         o.z = (v.z - mean) * rstd * g.z + b.z;
         o.w = (v.w - mean) * rstd * g.w + b.w;
-        out[(long long)n * out_batch_stride4 + j] = o;
+        store4(out + (long long)n * out_batch_stride + j * 4, o);
     }
 }
 
@@ -180,6 +203,12 @@ int vnext_stem_pool(const float *x, const float *bias, float *out, int N, int H,
     return VNEXT_OK;
 }
 
+size_t vnext_groupnorm_workspace_floats(int N, int HW, int groups) {
+    if (N <= 0 || HW <= 0 || groups <= 0) return 0;
+    const size_t nblk = (size_t)(HW + kGnRowsPerCta - 1) / kGnRowsPerCta;
+    return (nblk + 1) * (size_t)N * groups * 2;
+}
+
 int vnext_groupnorm_nhwc(const float *x, const float *gamma, const float *beta, float *out, long long out_batch_stride,
                          float *stats_ws, int N, int HW, int C, int groups, float eps, void *stream) {
     VNEXT_CHECK_ARG(N >= 0 && HW > 0 && C > 0 && groups > 0 && C == groups * 8 && C <= 1024 && kGnThreads % (C / 4) == 0,
@@ -187,14 +216,15 @@ int vnext_groupnorm_nhwc(const float *x, const float *gamma, const float *beta, 
     if (N == 0) return VNEXT_OK;
     VNEXT_CHECK_ARG(x && gamma && beta && out && stats_ws && out_batch_stride % 4 == 0, "vnext_groupnorm_nhwc: bad pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    VNEXT_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * N * groups, st));
-    const int rows_per_cta = 64;
-    dim3 grid((HW + rows_per_cta - 1) / rows_per_cta, N);
-    groupnorm_stats_kernel<<<grid, kGnThreads, 0, st>>>((const float4 *)x, stats_ws, HW, C, rows_per_cta);
+    const int nblk = (HW + kGnRowsPerCta - 1) / kGnRowsPerCta;
+    float *part = stats_ws + (size_t)N * groups * 2;          // [N][nblk][G][2] after the [N][G][2] (mean, rstd) table
+    dim3 grid(nblk, N);
+    groupnorm_partial_kernel<<<grid, kGnThreads, 0, st>>>((const float4 *)x, part, HW, C);
+    groupnorm_combine_kernel<<<N, ((groups + 31) / 32) * 32, 0, st>>>(part, stats_ws, nblk, HW, groups, eps);
     const long long total = (long long)N * HW * (C / 4);
-    groupnorm_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>((const float4 *)x, stats_ws, (const float4 *)gamma,
-                                                               (const float4 *)beta, (float4 *)out, N, HW, C,
-                                                               out_batch_stride / 4, eps);
+    groupnorm_apply_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float4 *)x, stats_ws, (const float4 *)gamma,
+                                                                      (const float4 *)beta, out, N, HW, C,
+                                                                      out_batch_stride, eps);
     count_launch(3);
     VNEXT_CUDA(cudaGetLastError());
     return VNEXT_OK;

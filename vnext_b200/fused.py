@@ -46,7 +46,7 @@ def groupnorm_nhwc(x, gamma, beta, groups=32, eps=1e-5, out=None, stats_ws=None)
         out = torch.empty_like(x)
     assert out.stride(2) == 1 and out.stride(1) == C
     if stats_ws is None:
-        stats_ws = torch.empty(2 * N * groups, dtype=torch.float32, device=x.device)
+        stats_ws = torch.empty(_cabi.lib().vnext_groupnorm_workspace_floats(N, HW, groups), dtype=torch.float32, device=x.device)
     info = {"bytes": 4.0 * x.numel() * 3}
     rc = _cabi.timed_call("groupnorm_nhwc", info, x, lambda: _cabi.lib().vnext_groupnorm_nhwc(
         x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), out.stride(0), stats_ws.data_ptr(), N, HW, C,

@@ -98,6 +98,13 @@ class SeqFormer(nn.Module):
             ori = (video.get("height", H), video.get("width", W))
             if len(pending) == depth:
                 yield finish()
+            if (len(frames), H, W, tuple(ori), n % depth) not in self._runners:
+                # a runner's construction (eager warm-up + graph capture) never overlaps a clip in flight: drain first,
+                # then build every slot of this geometry at once
+                while pending:
+                    yield finish()
+                for slot in range(depth):
+                    self.runner(len(frames), H, W, ori, slot=slot)
             run = self.runner(len(frames), H, W, ori, slot=n % depth)
             run.submit(frames_list=frames)
             pending.append((run, ori))

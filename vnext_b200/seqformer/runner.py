@@ -18,7 +18,10 @@ class ClipRunner:
         self.frames_dev = torch.zeros(T, 3, H, W, dtype=torch.uint8, device=dev)
         self.frames_pin = torch.zeros(T, 3, H, W, dtype=torch.uint8).pin_memory()
         self.stream = torch.cuda.Stream(device=dev)
+        # non-blocking stream: order it after whatever stream packed the engine's weights / built the ClipPlan
+        self.stream.wait_stream(torch.cuda.current_stream(dev))
         self.graph = None
+        self._pending = None
         with torch.cuda.device(dev):
             with torch.cuda.stream(self.stream):
                 for _ in range(2):                    # builds the ClipPlan, warms cuDNN/cuBLAS heuristics
@@ -61,6 +64,7 @@ class ClipRunner:
             self.frames_pin.copy_(frames_u8)
         scores_pin = torch.empty(self.scores.shape, dtype=self.scores.dtype, pin_memory=True)
         masks_pin = torch.empty(self.masks.shape, dtype=self.masks.dtype, pin_memory=True)
+        self.stream.wait_stream(torch.cuda.current_stream(self.frames_dev.device))
         with torch.cuda.stream(self.stream):
             self.frames_dev.copy_(self.frames_pin, non_blocking=True)
             self.run_device()
