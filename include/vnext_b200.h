@@ -97,7 +97,7 @@ int vnext_msda_forward_fused(int dtype, const void *value, const int64_t *spatia
  *   spatial_shapes_host / level_start_index_host: HOST copies of the int64 tensors (the TMA descriptors are built from
  *   them per call); levels must tile [0, spatial_size) in order.
  *   Front-end: either (sampling_loc, attn_weight) as vnext_msda_forward, or — when offsets_logits != NULL — the fused
- *   one of vnext_msda_forward_fused (offsets_logits, row_pitch, reference_points, ref_dim, ref_shared).
+ *   one of vnext_msda_forward_fused (offsets_logits, row_pitch, reference_points, ref_dim == 2, ref_shared).
  * Needs channels == 32, num_levels <= 4, num_levels*num_point in {8, 16, 32}, value fp32 or bf16 (16-byte aligned).
  */
 int vnext_msda_forward_selfattn(int dtype, const void *value, const int64_t *spatial_shapes_host,
@@ -164,6 +164,19 @@ int vnext_linear_tf32(const float *a, int lda, const float *weight, const float 
                       float *out, int ldo, int M, int N, int K, int flags, void *stream);
 
 /*
+ * Same kernel, operand / output formats chosen by the caller (bf16 activations end to end; BASELINE config 4):
+ *   in_dtype  (VNEXT_F32 | VNEXT_BF16): element type of `a` AND `weight` (fp32 -> kind::tf32, bf16 -> kind::f16 MMAs)
+ *   out_dtype (VNEXT_F32 | VNEXT_BF16): element type of `out` AND `residual`
+ * bias, bias2d, LayerNorm gamma/beta and all accumulation / statistics stay fp32.  bf16 rows (a, weight, out, residual)
+ * must be 16-byte aligned with pitches that are multiples of 8 elements.  The reference has no bf16 path; its AMP
+ * route is torch.autocast (detectron2/engine/train_loop.py:357-408).
+ */
+int vnext_linear_tc(int in_dtype, int out_dtype, const void *a, int lda, const void *weight, const float *bias,
+                    const float *bias2d, int bias_period, int ldb2, const unsigned char *row_mask, int mask_cols,
+                    const void *residual, int ldr, const float *ln_gamma, const float *ln_beta, float ln_eps, void *out,
+                    int ldo, int M, int N, int K, int flags, void *stream);
+
+/*
  * 3x3 convolution, stride 1, zero padding 1, NHWC fp32, as an implicit GEMM on the tcgen05 tensor cores (TF32) with
  * the folded-FrozenBN bias and ReLU fused: out[T,H,W,Cout] = act(conv3x3(x[T,H,W,Cin]) + bias).  Replaces the cuDNN
  * conv + BN-affine + ReLU passes of BottleneckBlock.conv2 (detectron2/modeling/backbone/resnet.py:150-161, 194-199)
@@ -173,6 +186,9 @@ int vnext_linear_tf32(const float *a, int lda, const float *weight, const float 
  */
 int vnext_conv3x3_tf32(const float *x, const float *weight_khwc, const float *bias, float *out, int T, int H, int W,
                        int Cin, int Cout, int relu, void *stream);
+/* dtype-generic form (see vnext_linear_tc): bf16 input needs Cin % 64 == 0, bf16 output Cout % 8 == 0. */
+int vnext_conv3x3_tc(int in_dtype, int out_dtype, const void *x, const void *weight_khwc, const float *bias, void *out,
+                     int T, int H, int W, int Cin, int Cout, int relu, void *stream);
 
 /*
  * Single-pass NHWC epilogues of the backbone / input projection (fp32, C % 4 == 0, 16-byte aligned):
@@ -195,6 +211,18 @@ int vnext_groupnorm_nhwc(const float *x, const float *gamma, const float *beta, 
                          void *stream);
 int vnext_preprocess(int in_is_u8, const void *frames, float *out, int T, int H, int W, int Hp, int Wp,
                      const float *mean3, const float *std3, void *stream);
+
+/* dtype-generic forms of the four kernels above (VNEXT_F32 | VNEXT_BF16 storage; bias / gamma / beta / statistics stay
+ * fp32): the bf16 activation path of the backbone and input projection. */
+int vnext_bias_act_dt(int dtype, const void *x, const float *bias, const void *residual, void *out, long long rows, int C,
+                      int relu, void *stream);
+int vnext_stem_pool_dt(int in_dtype, int out_dtype, const void *x, const float *bias, void *out, int N, int H, int W,
+                       int C, void *stream);
+int vnext_groupnorm_nhwc_dt(int in_dtype, int out_dtype, const void *x, const float *gamma, const float *beta, void *out,
+                            long long out_batch_stride, float *stats_ws, int N, int HW, int C, int groups, float eps,
+                            void *stream);
+int vnext_preprocess_dt(int in_is_u8, int out_dtype, const void *frames, void *out, int T, int H, int W, int Hp, int Wp,
+                        const float *mean3, const float *std3, void *stream);
 
 /*
  * Swin window attention, one kernel per block (projects/IDOL/idol/backbone/swin.py:129-169 WindowAttention.forward +

@@ -95,6 +95,46 @@ def test_tf32_mode_error_is_reported():
     assert max(errs.values()) < 2e-2
 
 
+def test_bf16_mode_error_is_reported():
+    """bf16 storage end to end (backbone, input projection, encoder, mask branch; BASELINE config 4's precision): within the
+    north star's 1e-2 of the fp32 oracle, relative to each output's scale."""
+    from vnext_b200.seqformer.engine import SeqFormerEngine
+    T, H, W, seed = 3, 96, 128, 0
+    sd = fill_state_dict(seqformer_r50_state_spec(), seed)
+    frames = synthetic_clip(T, H, W, seed)
+    out = SeqFormerEngine(sd, device="cuda", precision="bf16").inference(torch.stack(frames).cuda())
+    assert out["memory"].dtype == torch.bfloat16
+    with torch.no_grad():
+        ref = SO.inference(sd, frames, return_intermediates=True)
+    errs = {k: _rel(out[k].float().cpu(), ref[k]) for k in ("pred_logits", "pred_boxes", "pred_masks")}
+    errs["memory"] = _rel(out["memory"].float().cpu(), ref["memory"][0])
+    print("bf16 relative errors:", errs)
+    assert max(errs.values()) < 1e-2
+
+
+@pytest.mark.parametrize("geom", ["480x864", "720x1280"])
+def test_full_size_parity_of_the_benchmarked_modes(geom):
+    """The modes bench.py times (tf32, bf16), at the BASELINE geometries (T=5), against the CPU oracle on the same clip:
+    dense outputs within 1e-2 of each tensor's scale, identical top-10 instances, mask agreement > 0.99."""
+    from vnext_b200.seqformer.engine import SeqFormerEngine
+    H, W = (480, 864) if geom == "480x864" else (720, 1280)
+    T = 5
+    sd = fill_state_dict(seqformer_r50_state_spec(), 0)
+    frames = synthetic_clip(T, H, W, 0)
+    with torch.no_grad():
+        ref = SO.inference(sd, frames)
+    top_ref = ref["pred_logits"][0].sigmoid().max(1)[0].topk(10)[1]
+    for precision in ("tf32", "bf16"):
+        out = SeqFormerEngine(sd, device="cuda", precision=precision).inference(torch.stack(frames).cuda())
+        errs = {k: _rel(out[k].float().cpu(), ref[k]) for k in ("pred_logits", "pred_boxes", "pred_masks")}
+        top = out["pred_logits"][0].sigmoid().max(1)[0].topk(10)[1].cpu()
+        same = len(set(top.tolist()) & set(top_ref.tolist()))
+        agree = ((out["pred_masks"][0, top_ref.cuda()].float().cpu() > 0) == (ref["pred_masks"][0, top_ref] > 0)).float().mean().item()
+        print(f"{geom} {precision}: rel errors {errs}; top-10 overlap {same}/10; mask agreement {agree:.5f}")
+        assert max(errs.values()) < 1e-2, (precision, errs)
+        assert same >= 9 and agree > 0.99
+
+
 def test_clip_matching_inference_long_video():
     """CLIP_MATCHING: True — sliding clips through the engine, stitched on the device; against the CPU oracle run on the
     same windows + the (reference-pinned) clip tracker."""

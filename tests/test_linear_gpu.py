@@ -98,3 +98,84 @@ def test_conv3x3_implicit_gemm(T, H, W, Cin, Cout):
     assert (out.double() - ref).abs().max().item() < tol
     out = conv3x3(x, wk, b, relu=True)
     assert (out.double() - ref.clamp(min=0)).abs().max().item() < tol
+
+
+# ---------------------------------------------------------------------------------------------- bf16 operands / outputs
+def _ref_bf16(x, w, b):
+    """fp64 reference on the bf16-ROUNDED operands (what the tensor cores see); accumulation is fp32 in TMEM."""
+    return F.linear(x.bfloat16().double(), w.bfloat16().double(), None if b is None else b.double())
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 256), (300, 256, 256), (1000, 384, 256), (97800, 256, 256),
+                                   (4097, 1024, 256), (513, 256, 1024), (77, 64, 64), (1500, 128, 2048), (2000, 640, 256),
+                                   (300, 384, 64), (130, 256, 136)])
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_bf16_operands(M, N, K, out_dtype):
+    from vnext_b200.linear import linear
+    x, w, b = _mk(M, N, K, 11)
+    ref = _ref_bf16(x, w, b)
+    out = linear(x.bfloat16(), w.bfloat16(), b, out_dtype=out_dtype)
+    assert out.dtype == out_dtype
+    scale = ref.abs().max().item()
+    # fp32 out: only accumulation-order error; bf16 out: one output rounding (2^-9 relative)
+    tol = 2e-5 * scale if out_dtype == torch.float32 else 5e-3 * scale
+    assert (out.double() - ref).abs().max().item() < tol
+    out_r = linear(x.bfloat16(), w.bfloat16(), b, relu=True, out_dtype=out_dtype)
+    assert (out_r.double() - ref.clamp(min=0)).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("M,K", [(128, 256), (333, 1024), (97800, 256)])
+def test_bf16_residual_layernorm_epilogue(M, K):
+    from vnext_b200.linear import linear
+    x, w, b = _mk(M, 256, K, 1)
+    g = torch.Generator().manual_seed(2)
+    res = torch.randn(M, 256, generator=g).cuda().bfloat16()
+    gamma = (torch.rand(256, generator=g) + 0.5).cuda()
+    beta = (torch.randn(256, generator=g) * 0.1).cuda()
+    ref = F.layer_norm(res.double() + _ref_bf16(x, w, b), (256,), gamma.double(), beta.double(), 1e-5)
+    out = linear(x.bfloat16(), w.bfloat16(), b, residual=res, ln_weight=gamma, ln_bias=beta)
+    assert out.dtype == torch.bfloat16
+    assert (out.double() - ref).abs().max().item() < 3e-2          # one bf16 rounding of O(4) outputs
+    assert (out.double() - ref).abs().mean().item() < 3e-3
+    out32 = linear(x.bfloat16(), w.bfloat16(), b, residual=res.float(), ln_weight=gamma, ln_bias=beta, out_dtype=torch.float32)
+    assert (out32.double() - ref).abs().max().item() < 1e-4
+
+
+def test_bf16_bias2d_row_mask_residual_relu_and_mixed_fp32_input():
+    from vnext_b200.linear import linear
+    M, N, K, S = 1000, 384, 256, 250
+    x, w, b = _mk(M, N, K, 5)
+    g = torch.Generator().manual_seed(6)
+    res = torch.randn(M, N, generator=g).cuda().bfloat16()
+    b2 = torch.randn(S, N, generator=g).cuda()
+    mask = (torch.rand(S, generator=g) < 0.3).to(torch.uint8).cuda()
+    ref = _ref_bf16(x, w, b)
+    scale = ref.abs().max().item()
+    out = linear(x.bfloat16(), w.bfloat16(), b, relu=True, residual=res)
+    assert (out.double() - (ref + res.double()).clamp(min=0)).abs().max().item() < 8e-3 * scale
+    out = linear(x.bfloat16(), w.bfloat16(), None, bias2d=b2, out_dtype=torch.float32)      # the offsets|logits projection
+    want = _ref_bf16(x, w, None) + b2.double().repeat(M // S, 1)
+    assert (out.double() - want).abs().max().item() < 2e-5 * scale
+    out = linear(x.bfloat16(), w.bfloat16(), b, row_mask=mask, mask_cols=256)               # the value projection
+    rows = mask.bool().repeat(M // S)
+    assert (out[rows, :256] == 0).all() and (out.double()[~rows] - ref[~rows]).abs().max().item() < 5e-3 * scale
+    out = linear(x, w, b, out_dtype=torch.bfloat16)                                          # fp32 (TF32) in, bf16 out
+    ref32 = F.linear(x.double(), w.double(), b.double())
+    assert out.dtype == torch.bfloat16 and (out.double() - ref32).abs().max().item() < 6e-3 * scale
+
+
+@pytest.mark.parametrize("T,H,W,Cin,Cout", [(2, 23, 40, 64, 64), (1, 8, 16, 64, 128), (3, 46, 80, 256, 256),
+                                           (1, 184, 320, 64, 64), (2, 13, 17, 128, 8), (5, 92, 160, 256, 64)])
+def test_conv3x3_bf16(T, H, W, Cin, Cout):
+    from vnext_b200.linear import conv3x3
+    g = torch.Generator().manual_seed(T * 1000 + H)
+    x = torch.randn(T, H, W, Cin, generator=g).cuda().bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5).cuda().bfloat16()
+    b = torch.randn(Cout, generator=g).cuda()
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), padding=1).permute(0, 2, 3, 1)
+    scale = ref.abs().max().item()
+    out = conv3x3(x, wk, b, relu=False, out_dtype=torch.float32)
+    assert (out.double() - ref).abs().max().item() < 2e-5 * scale
+    out = conv3x3(x, wk, b, relu=True)
+    assert out.dtype == torch.bfloat16 and (out.double() - ref.clamp(min=0)).abs().max().item() < 5e-3 * scale

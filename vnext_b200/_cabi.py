@@ -20,11 +20,17 @@ SIGNATURES = {
     "vnext_msda_forward": (_c_int, [_c_int] + [_c_void_p] * 5 + [_c_int] * 7 + [_c_void_p, _c_void_p]),
     "vnext_msda_forward_fused": (_c_int, [_c_int] + [_c_void_p] * 4 + [_c_int, _c_void_p, _c_int, _c_int] + [_c_int] * 7
                                  + [_c_void_p, _c_void_p]),
+    "vnext_msda_forward_selfattn": (_c_int, [_c_int] + [_c_void_p] * 6 + [_c_int, _c_void_p, _c_int, _c_int] + [_c_int] * 7
+                                    + [_c_void_p, _c_void_p]),
     "vnext_msda_backward": (_c_int, [_c_int] + [_c_void_p] * 6 + [_c_int] * 7 + [_c_void_p] * 5),
     "vnext_msda_backward_workspace_bytes": (_c_size_t, [_c_int] * 5),
     "vnext_linear_tf32": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_int,
                                    _c_void_p, _c_int, _c_void_p, _c_void_p, ctypes.c_float, _c_void_p, _c_int,
                                    _c_int, _c_int, _c_int, _c_int, _c_void_p]),
+    "vnext_linear_tc": (_c_int, [_c_int, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p,
+                                 _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, ctypes.c_float, _c_void_p, _c_int,
+                                 _c_int, _c_int, _c_int, _c_int, _c_void_p]),
+    "vnext_conv3x3_tc": (_c_int, [_c_int, _c_int] + [_c_void_p] * 4 + [_c_int] * 6 + [_c_void_p]),
     "vnext_conv3x3_tf32": (_c_int, [_c_void_p] * 4 + [_c_int] * 6 + [_c_void_p]),
     "vnext_bias_act": (_c_int, [_c_void_p] * 4 + [ctypes.c_longlong, _c_int, _c_int, _c_void_p]),
     "vnext_stem_pool": (_c_int, [_c_void_p] * 3 + [_c_int] * 4 + [_c_void_p]),
@@ -32,6 +38,11 @@ SIGNATURES = {
     "vnext_groupnorm_nhwc": (_c_int, [_c_void_p] * 4 + [ctypes.c_longlong, _c_void_p, _c_int, _c_int, _c_int, _c_int,
                                       ctypes.c_float, _c_void_p]),
     "vnext_preprocess": (_c_int, [_c_int, _c_void_p, _c_void_p] + [_c_int] * 5 + [_c_void_p, _c_void_p, _c_void_p]),
+    "vnext_bias_act_dt": (_c_int, [_c_int] + [_c_void_p] * 4 + [ctypes.c_longlong, _c_int, _c_int, _c_void_p]),
+    "vnext_stem_pool_dt": (_c_int, [_c_int, _c_int] + [_c_void_p] * 3 + [_c_int] * 4 + [_c_void_p]),
+    "vnext_groupnorm_nhwc_dt": (_c_int, [_c_int, _c_int] + [_c_void_p] * 4 + [ctypes.c_longlong, _c_void_p, _c_int, _c_int,
+                                                                  _c_int, _c_int, ctypes.c_float, _c_void_p]),
+    "vnext_preprocess_dt": (_c_int, [_c_int, _c_int, _c_void_p, _c_void_p] + [_c_int] * 5 + [_c_void_p, _c_void_p, _c_void_p]),
     "vnext_swin_window_attention": (_c_int, [_c_void_p] * 4 + [_c_int] * 7 + [_c_void_p]),
     "vnext_swin_window_attention_tc": (_c_int, [_c_void_p] * 4 + [_c_int] * 7 + [_c_void_p]),
     "vnext_layernorm": (_c_int, [_c_void_p] * 4 + [ctypes.c_longlong, _c_int, ctypes.c_float, _c_void_p]),

@@ -39,6 +39,12 @@ int msda_backward_device(int dtype, const void *value, const int64_t *shapes, co
                          const void *attn, const void *gout, int N, int S, int M, int D, int L, int Lq, int K,
                          void *gvalue, void *gloc, void *gattn, void *workspace, cudaStream_t stream);
 
+bool msda_window_supported(int dtype, int D, int L, int K);
+int msda_forward_window_device(int dtype, const void *value, const int64_t *hshapes, const int64_t *hlsi, const float *loc,
+                               const float *attn, const float *oa, int oa_pitch, const float *ref, int ref_dim,
+                               int ref_shared, int N, int S, int M, int L, int K, int margin, void *out,
+                               cudaStream_t stream);
+
 int msda_forward_fused_device(int dtype, const void *value, const int64_t *shapes, const int64_t *lsi, const float *oa,
                               int oa_pitch, int n_off, const float *ref, int ref_dim, int ref_shared, int N, int S,
                               int M, int D, int L, int Lq, int K, void *out, cudaStream_t stream);

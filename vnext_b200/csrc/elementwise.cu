@@ -10,27 +10,29 @@
 
 namespace vnext {
 
-// out = act(x + bias[c] (+ residual))   rows x C, C % 4 == 0
-__global__ void __launch_bounds__(256) bias_act_kernel(const float4 *__restrict__ x, const float4 *__restrict__ bias,
-                                                       const float4 *__restrict__ residual, float4 *__restrict__ out,
+// out = act(x + bias[c] (+ residual))   rows x C, C % 4 == 0; T = storage type of x / residual / out (fp32 or bf16)
+template <typename T>
+__global__ void __launch_bounds__(256) bias_act_kernel(const T *__restrict__ x, const float4 *__restrict__ bias,
+                                                       const T *__restrict__ residual, T *__restrict__ out,
                                                        long long n4, int c4, int relu) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        float4 v = x[i];
+        float4 v = load4(x + i * 4);
         const float4 b = __ldg(bias + (int)(i % c4));
         v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
         if (residual) {
-            const float4 r = residual[i];
+            const float4 r = load4(residual + i * 4);
             v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
         }
         if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-        out[i] = v;
+        store4(out + i * 4, v);
     }
 }
 
 // Stem tail: out[n, ho, wo, c] = max over the 3x3 / stride 2 / pad 1 window of relu(x + bias[c]).
 // relu and +bias are monotone, so this is relu(max(x) + bias): one read of the conv output, one quarter-size write.
-__global__ void __launch_bounds__(256) stem_pool_kernel(const float4 *__restrict__ x, const float4 *__restrict__ bias,
-                                                        float4 *__restrict__ out, int N, int H, int W, int Ho, int Wo,
+template <typename IT, typename OT>
+__global__ void __launch_bounds__(256) stem_pool_kernel(const IT *__restrict__ x, const float4 *__restrict__ bias,
+                                                        OT *__restrict__ out, int N, int H, int W, int Ho, int Wo,
                                                         int c4) {
     const long long total = (long long)N * Ho * Wo * c4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -49,13 +51,13 @@ __global__ void __launch_bounds__(256) stem_pool_kernel(const float4 *__restrict
             for (int dx = 0; dx < 3; ++dx) {
                 const int w = 2 * wo - 1 + dx;
                 if (w < 0 || w >= W) continue;
-                const float4 v = x[((long long)(n * H + h) * W + w) * c4 + c];
+                const float4 v = load4(x + (((long long)(n * H + h) * W + w) * c4 + c) * 4);
                 m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
             }
         }
         const float4 b = __ldg(bias + c);
         m.x = fmaxf(m.x + b.x, 0.f); m.y = fmaxf(m.y + b.y, 0.f); m.z = fmaxf(m.z + b.z, 0.f); m.w = fmaxf(m.w + b.w, 0.f);
-        out[i] = m;
+        store4(out + i * 4, m);
     }
 }
 
@@ -66,7 +68,8 @@ __global__ void __launch_bounds__(256) stem_pool_kernel(const float4 *__restrict
 // variance does not suffer the E[x^2] - mean^2 cancellation over the whole level.
 constexpr int kGnThreads = 256;
 constexpr int kGnRowsPerCta = 64;
-__global__ void __launch_bounds__(kGnThreads) groupnorm_partial_kernel(const float4 *__restrict__ x, float *__restrict__ part,
+template <typename IT>
+__global__ void __launch_bounds__(kGnThreads) groupnorm_partial_kernel(const IT *__restrict__ x, float *__restrict__ part,
                                                                        int HW, int C) {
     // thread -> (row offset, float4 column); C/4 float4 columns, two per 8-channel group
     const int c4 = C / 4;
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(kGnThreads) groupnorm_partial_kernel(const flo
     const int r1 = min(HW, r0 + kGnRowsPerCta);
     float s = 0.f, ss = 0.f;
     for (int r = r0 + rsub; r < r1; r += rstep) {
-        const float4 v = x[((long long)n * HW + r) * c4 + col];
+        const float4 v = load4(x + (((long long)n * HW + r) * c4 + col) * 4);
         s += (v.x + v.y) + (v.z + v.w);
         ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
     }
@@ -118,8 +121,8 @@ __global__ void groupnorm_combine_kernel(const float *__restrict__ part, float *
     stats[((long long)n * G + g) * 2 + 1] = (float)(1.0 / sqrt(m2 / cnt + (double)eps));
 }
 
-template <typename OT>
-__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float4 *__restrict__ x, const float *__restrict__ stats,
+template <typename IT, typename OT>
+__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const IT *__restrict__ x, const float *__restrict__ stats,
                                                               const float4 *__restrict__ gamma, const float4 *__restrict__ beta,
                                                               OT *__restrict__ out, int N, int HW, int C,
                                                               long long out_batch_stride, float eps) {
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float4 *__re
         const int col = (int)(j % c4);
         const float *st = stats + ((long long)n * G + col / 2) * 2;
         const float mean = st[0], rstd = st[1];
-        const float4 v = x[i], g = __ldg(gamma + col), b = __ldg(beta + col);
+        const float4 v = load4(x + i * 4), g = __ldg(gamma + col), b = __ldg(beta + col);
         float4 o;
         o.x = (v.x - mean) * rstd * g.x + b.x;
         o.y = (v.y - mean) * rstd * g.y + b.y;
@@ -142,8 +145,8 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float4 *__re
 }
 
 // uint8 / float frames [T, 3, H, W] (planar, 0..255) -> normalised, zero-padded channels-last [T, Hp, Wp, 3]
-template <typename T>
-__global__ void __launch_bounds__(256) preprocess_kernel(const T *__restrict__ in, float *__restrict__ out, int Tn, int H,
+template <typename T, typename OT>
+__global__ void __launch_bounds__(256) preprocess_kernel(const T *__restrict__ in, OT *__restrict__ out, int Tn, int H,
                                                          int W, int Hp, int Wp, float m0, float m1, float m2, float s0,
                                                          float s1, float s2) {
     const long long total = (long long)Tn * Hp * Wp;
@@ -158,9 +161,9 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const T *__restrict__ i
             g = ((float)in[base + (long long)H * W] - m1) / s1;
             b = ((float)in[base + 2ll * H * W] - m2) / s2;
         }
-        out[i * 3] = r;
-        out[i * 3 + 1] = g;
-        out[i * 3 + 2] = b;
+        out[i * 3] = (OT)r;
+        out[i * 3 + 1] = (OT)g;
+        out[i * 3 + 2] = (OT)b;
     }
 }
 
@@ -174,33 +177,71 @@ static inline int grid_for(long long work_items, int threads) {
 
 using namespace vnext;
 
+template <typename IT, typename OT>
+static void groupnorm_launch(const void *x, const float *gamma, const float *beta, void *out, long long out_batch_stride,
+                             float *stats_ws, int N, int HW, int C, int groups, float eps, cudaStream_t st) {
+    const int nblk = (HW + kGnRowsPerCta - 1) / kGnRowsPerCta;
+    float *part = stats_ws + (size_t)N * groups * 2;          // [N][nblk][G][2] after the [N][G][2] (mean, rstd) table
+    dim3 grid(nblk, N);
+    groupnorm_partial_kernel<IT><<<grid, kGnThreads, 0, st>>>((const IT *)x, part, HW, C);
+    groupnorm_combine_kernel<<<N, ((groups + 31) / 32) * 32, 0, st>>>(part, stats_ws, nblk, HW, groups, eps);
+    const long long total = (long long)N * HW * (C / 4);
+    groupnorm_apply_kernel<IT, OT><<<grid_for(total, 256), 256, 0, st>>>((const IT *)x, stats_ws, (const float4 *)gamma,
+                                                                       (const float4 *)beta, (OT *)out, N, HW, C,
+                                                                       out_batch_stride, eps);
+}
+
 extern "C" {
 
-int vnext_bias_act(const float *x, const float *bias, const float *residual, float *out, long long rows, int C, int relu,
-                   void *stream) {
+static inline bool dt_ok(int dt) { return dt == VNEXT_F32 || dt == VNEXT_BF16; }
+
+int vnext_bias_act_dt(int dtype, const void *x, const float *bias, const void *residual, void *out, long long rows, int C,
+                      int relu, void *stream) {
+    VNEXT_CHECK_ARG(dt_ok(dtype), "vnext_bias_act: dtype must be fp32 or bf16");
     VNEXT_CHECK_ARG(rows >= 0 && C > 0 && C % 4 == 0, "vnext_bias_act: C must be a positive multiple of 4 (got %d)", C);
     if (rows == 0) return VNEXT_OK;
     VNEXT_CHECK_ARG(x && bias && out, "vnext_bias_act: null pointer");
     const long long n4 = rows * (C / 4);
-    bias_act_kernel<<<grid_for(n4, 256), 256, 0, (cudaStream_t)stream>>>((const float4 *)x, (const float4 *)bias,
-                                                                       (const float4 *)residual, (float4 *)out, n4, C / 4,
-                                                                       relu);
+    if (dtype == VNEXT_F32)
+        bias_act_kernel<float><<<grid_for(n4, 256), 256, 0, (cudaStream_t)stream>>>(
+            (const float *)x, (const float4 *)bias, (const float *)residual, (float *)out, n4, C / 4, relu);
+    else
+        bias_act_kernel<__nv_bfloat16><<<grid_for(n4, 256), 256, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16 *)x, (const float4 *)bias, (const __nv_bfloat16 *)residual, (__nv_bfloat16 *)out, n4, C / 4, relu);
     count_launch();
     VNEXT_CUDA(cudaGetLastError());
     return VNEXT_OK;
 }
+int vnext_bias_act(const float *x, const float *bias, const float *residual, float *out, long long rows, int C, int relu,
+                   void *stream) {
+    return vnext_bias_act_dt(VNEXT_F32, x, bias, residual, out, rows, C, relu, stream);
+}
 
-int vnext_stem_pool(const float *x, const float *bias, float *out, int N, int H, int W, int C, void *stream) {
+int vnext_stem_pool_dt(int in_dtype, int out_dtype, const void *x, const float *bias, void *out, int N, int H, int W, int C,
+                       void *stream) {
+    VNEXT_CHECK_ARG(dt_ok(in_dtype) && dt_ok(out_dtype), "vnext_stem_pool: dtypes must be fp32 or bf16");
     VNEXT_CHECK_ARG(N >= 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "vnext_stem_pool: bad shape");
     if (N == 0) return VNEXT_OK;
     VNEXT_CHECK_ARG(x && bias && out, "vnext_stem_pool: null pointer");
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const long long total = (long long)N * Ho * Wo * (C / 4);
-    stem_pool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const float4 *)x, (const float4 *)bias,
-                                                                           (float4 *)out, N, H, W, Ho, Wo, C / 4);
+    const int g = grid_for(total, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float4 *b4 = (const float4 *)bias;
+    if (in_dtype == VNEXT_F32 && out_dtype == VNEXT_F32)
+        stem_pool_kernel<float, float><<<g, 256, 0, st>>>((const float *)x, b4, (float *)out, N, H, W, Ho, Wo, C / 4);
+    else if (in_dtype == VNEXT_F32)
+        stem_pool_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float *)x, b4, (__nv_bfloat16 *)out, N, H, W, Ho, Wo, C / 4);
+    else if (out_dtype == VNEXT_F32)
+        stem_pool_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16 *)x, b4, (float *)out, N, H, W, Ho, Wo, C / 4);
+    else
+        stem_pool_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16 *)x, b4, (__nv_bfloat16 *)out, N, H, W, Ho, Wo, C / 4);
     count_launch();
     VNEXT_CUDA(cudaGetLastError());
     return VNEXT_OK;
+}
+int vnext_stem_pool(const float *x, const float *bias, float *out, int N, int H, int W, int C, void *stream) {
+    return vnext_stem_pool_dt(VNEXT_F32, VNEXT_F32, x, bias, out, N, H, W, C, stream);
 }
 
 size_t vnext_groupnorm_workspace_floats(int N, int HW, int groups) {
@@ -209,42 +250,57 @@ size_t vnext_groupnorm_workspace_floats(int N, int HW, int groups) {
     return (nblk + 1) * (size_t)N * groups * 2;
 }
 
-int vnext_groupnorm_nhwc(const float *x, const float *gamma, const float *beta, float *out, long long out_batch_stride,
-                         float *stats_ws, int N, int HW, int C, int groups, float eps, void *stream) {
+int vnext_groupnorm_nhwc_dt(int in_dtype, int out_dtype, const void *x, const float *gamma, const float *beta, void *out,
+                            long long out_batch_stride, float *stats_ws, int N, int HW, int C, int groups, float eps,
+                            void *stream) {
+    VNEXT_CHECK_ARG(dt_ok(in_dtype) && dt_ok(out_dtype), "vnext_groupnorm_nhwc: dtypes must be fp32 or bf16");
     VNEXT_CHECK_ARG(N >= 0 && HW > 0 && C > 0 && groups > 0 && C == groups * 8 && C <= 1024 && kGnThreads % (C / 4) == 0,
                     "vnext_groupnorm_nhwc: supports C == 8*groups with C/4 dividing 256 (got C=%d groups=%d)", C, groups);
     if (N == 0) return VNEXT_OK;
     VNEXT_CHECK_ARG(x && gamma && beta && out && stats_ws && out_batch_stride % 4 == 0, "vnext_groupnorm_nhwc: bad pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    const int nblk = (HW + kGnRowsPerCta - 1) / kGnRowsPerCta;
-    float *part = stats_ws + (size_t)N * groups * 2;          // [N][nblk][G][2] after the [N][G][2] (mean, rstd) table
-    dim3 grid(nblk, N);
-    groupnorm_partial_kernel<<<grid, kGnThreads, 0, st>>>((const float4 *)x, part, HW, C);
-    groupnorm_combine_kernel<<<N, ((groups + 31) / 32) * 32, 0, st>>>(part, stats_ws, nblk, HW, groups, eps);
-    const long long total = (long long)N * HW * (C / 4);
-    groupnorm_apply_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float4 *)x, stats_ws, (const float4 *)gamma,
-                                                                      (const float4 *)beta, out, N, HW, C,
-                                                                      out_batch_stride, eps);
+    if (in_dtype == VNEXT_F32 && out_dtype == VNEXT_F32)
+        groupnorm_launch<float, float>(x, gamma, beta, out, out_batch_stride, stats_ws, N, HW, C, groups, eps, st);
+    else if (in_dtype == VNEXT_F32)
+        groupnorm_launch<float, __nv_bfloat16>(x, gamma, beta, out, out_batch_stride, stats_ws, N, HW, C, groups, eps, st);
+    else if (out_dtype == VNEXT_F32)
+        groupnorm_launch<__nv_bfloat16, float>(x, gamma, beta, out, out_batch_stride, stats_ws, N, HW, C, groups, eps, st);
+    else
+        groupnorm_launch<__nv_bfloat16, __nv_bfloat16>(x, gamma, beta, out, out_batch_stride, stats_ws, N, HW, C, groups, eps, st);
     count_launch(3);
     VNEXT_CUDA(cudaGetLastError());
     return VNEXT_OK;
 }
+int vnext_groupnorm_nhwc(const float *x, const float *gamma, const float *beta, float *out, long long out_batch_stride,
+                         float *stats_ws, int N, int HW, int C, int groups, float eps, void *stream) {
+    return vnext_groupnorm_nhwc_dt(VNEXT_F32, VNEXT_F32, x, gamma, beta, out, out_batch_stride, stats_ws, N, HW, C, groups, eps,
+                                   stream);
+}
 
-int vnext_preprocess(int in_is_u8, const void *frames, float *out, int T, int H, int W, int Hp, int Wp, const float *mean3,
-                     const float *std3, void *stream) {
+int vnext_preprocess_dt(int in_is_u8, int out_dtype, const void *frames, void *out, int T, int H, int W, int Hp, int Wp,
+                        const float *mean3, const float *std3, void *stream) {
+    VNEXT_CHECK_ARG(dt_ok(out_dtype), "vnext_preprocess: out dtype must be fp32 or bf16");
     VNEXT_CHECK_ARG(T >= 0 && H > 0 && W > 0 && Hp >= H && Wp >= W, "vnext_preprocess: bad shape");
     if (T == 0) return VNEXT_OK;
     VNEXT_CHECK_ARG(frames && out && mean3 && std3, "vnext_preprocess: null pointer");
     const long long total = (long long)T * Hp * Wp;
-    if (in_is_u8)
-        preprocess_kernel<unsigned char><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-            (const unsigned char *)frames, out, T, H, W, Hp, Wp, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]);
-    else
-        preprocess_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-            (const float *)frames, out, T, H, W, Hp, Wp, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]);
+    const int g = grid_for(total, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+#define VNEXT_PP(IT, OT)                                                                                              \
+    preprocess_kernel<IT, OT><<<g, 256, 0, st>>>((const IT *)frames, (OT *)out, T, H, W, Hp, Wp, mean3[0], mean3[1], \
+                                                 mean3[2], std3[0], std3[1], std3[2])
+    if (in_is_u8 && out_dtype == VNEXT_F32) VNEXT_PP(unsigned char, float);
+    else if (in_is_u8) VNEXT_PP(unsigned char, __nv_bfloat16);
+    else if (out_dtype == VNEXT_F32) VNEXT_PP(float, float);
+    else VNEXT_PP(float, __nv_bfloat16);
+#undef VNEXT_PP
     count_launch();
     VNEXT_CUDA(cudaGetLastError());
     return VNEXT_OK;
+}
+int vnext_preprocess(int in_is_u8, const void *frames, float *out, int T, int H, int W, int Hp, int Wp, const float *mean3,
+                     const float *std3, void *stream) {
+    return vnext_preprocess_dt(in_is_u8, VNEXT_F32, frames, out, T, H, W, Hp, Wp, mean3, std3, stream);
 }
 
 }  // extern "C"

@@ -3,9 +3,11 @@
 //   out[M, N] = epilogue( A[M, K] . B[N, K]^T + bias[N] )
 //
 // A = activations (tokens or NHWC pixels, K contiguous), B = the nn.Linear / 1x1-conv weight exactly as
-// the checkpoint stores it ([out, in], K contiguous).  fp32 storage, TF32 tensor-core math with fp32
-// accumulation in TMEM (kind::tf32) — the precision PyTorch's own conv path uses on this GPU; a bf16
-// instantiation shares the code.
+// the checkpoint stores it ([out, in], K contiguous).  Two operand formats share the code (template KIND):
+//   KIND 0: fp32 storage, TF32 tensor-core math (kind::tf32) — the precision PyTorch's own conv path uses on this GPU;
+//   KIND 1: bf16 storage (activations + a bf16 copy of the weight), kind::f16 with bf16 operands.
+// Accumulation is fp32 in TMEM either way; the output (and the residual read by the epilogue) is fp32 or bf16 (OutT),
+// bias / LayerNorm parameters / statistics stay fp32.
 //
 // Replaces the cuBLAS GEMM + separate bias / ReLU / residual-add / LayerNorm kernels of the reference's
 // projection and FFN layers (projects/SeqFormer/seqformer/models/deformable_transformer.py:155-169,
@@ -136,6 +138,11 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+
 // K-major operand tile in shared memory, 128-byte rows, SWIZZLE_128B (8 rows x 128 B = 1024-B atoms):
 //   start address >> 4 | LBO (ignored for swizzled K-major) = 1 | SBO = 1024 B between 8-row groups | version 1 | layout 2
 __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
@@ -211,18 +218,19 @@ __device__ __forceinline__ void epilogue_add_global(const GemmParams &p, int row
     }
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int KIND, bool OUT16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
-                 const GemmParams p) {
-    constexpr int BLOCK_K = 32;                 // fp32 elements = 128 bytes = one swizzle row
-    constexpr int UMMA_K = 8;                   // 32 bytes of tf32
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
+               const GemmParams p) {
+    constexpr int BLOCK_K = KIND == 0 ? 32 : 64;   // elements per 128-byte swizzle row (fp32 / bf16)
+    constexpr int UMMA_K = KIND == 0 ? 8 : 16;     // 32 bytes per MMA either way
     constexpr int A_BYTES = BLOCK_M * 128, B_BYTES = BLOCK_N * 128;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int ACC_STAGES = 2;
     constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;          // 256 or 512: power of two >= 32
-    constexpr uint32_t IDESC = make_idesc(2, BLOCK_M, BLOCK_N);
+    constexpr uint32_t IDESC = make_idesc(KIND == 0 ? 2 : 1, BLOCK_M, BLOCK_N);   // a/b format: 2 = TF32, 1 = BF16
+    constexpr uint32_t EPI_TILE_BYTES = OUT16 ? 2048u : 4096u;   // 32 rows x 32 columns of OutT
     static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
 
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -318,7 +326,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const uint64_t da = make_smem_desc_sw128(sa), db = make_smem_desc_sw128(sb);
 #pragma unroll
                 for (int k = 0; k < BLOCK_K / UMMA_K; ++k)   // advance 32 B inside the 128-B swizzle row: +2 in 16-B units
-                    umma<0>(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0);
+                    umma<KIND>(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0);
                 if (csize > 1) umma_commit_mcast(&empty_bar[stage], (uint16_t)3);   // frees the slot in BOTH CTAs
                 else umma_commit(&empty_bar[stage]);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -341,6 +349,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         unsigned char *const buf0 = epi_smem + ewi * 8192;
         unsigned char *const buf1 = buf0 + 4096;
         const int swz = lane & 7;                                   // 16-B chunk j of row r lives at j ^ (r & 7)
+        const int swz64 = (lane >> 1) & 3;                          // same for the 64-B rows of a bf16 tile
         uint32_t stores = 0, res_loads = 0;
         int bias_n_idx = -1;
         if (tma_epi && lane == 0) {
@@ -370,7 +379,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             if (tma_epi && has_res && half < n_chunks) {                // first residual tile: in flight while we wait
                 if (lane == 0) {
-                    mbar_expect_tx(&res_bar[ewi], 4096);
+                    mbar_expect_tx(&res_bar[ewi], EPI_TILE_BYTES);
                     tma_load_2d(buf1, &tmap_res, n_idx + half * 32, row0, &res_bar[ewi]);
                 }
             }
@@ -395,7 +404,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         if (tma_epi && has_res) {
                             mbar_wait(&res_bar[ewi], res_loads & 1);
                             ++res_loads;
-                            rrow = buf1 + lane * 128;
+                            rrow = buf1 + lane * (OUT16 ? 64 : 128);
                         }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {                    // bias from shared memory (broadcast reads)
@@ -403,7 +412,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             float4 x = make_float4(__uint_as_float(v[4 * j]) + b.x, __uint_as_float(v[4 * j + 1]) + b.y,
                                                    __uint_as_float(v[4 * j + 2]) + b.z, __uint_as_float(v[4 * j + 3]) + b.w);
                             if (rrow) {
-                                const float4 r = *reinterpret_cast<const float4 *>(rrow + ((j ^ swz) << 4));
+                                float4 r;
+                                if (OUT16)     // 64-B rows, SWIZZLE_64B: 16-B chunk c of row r lives at c ^ ((r >> 1) & 3)
+                                    r = load4(reinterpret_cast<const __nv_bfloat16 *>(rrow + (((j >> 1) ^ swz64) << 4) + (j & 1) * 8));
+                                else
+                                    r = *reinterpret_cast<const float4 *>(rrow + ((j ^ swz) << 4));
                                 x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
                             }
                             v[4 * j] = __float_as_uint(x.x); v[4 * j + 1] = __float_as_uint(x.y);
@@ -412,7 +425,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         if (rrow) {
                             __syncwarp();                                // tile consumed by all lanes -> refill it
                             if (lane == 0 && c + 2 < n_chunks) {
-                                mbar_expect_tx(&res_bar[ewi], 4096);
+                                mbar_expect_tx(&res_bar[ewi], EPI_TILE_BYTES);
                                 tma_load_2d(buf1, &tmap_res, col0 + 64, row0, &res_bar[ewi]);
                             }
                         }
@@ -465,11 +478,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             }
                             __syncwarp();
                         }
+                        if (OUT16) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            *reinterpret_cast<float4 *>(ob + lane * 128 + ((j ^ swz) << 4)) =
-                                make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                            __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                            for (int j = 0; j < 4; ++j) {
+                                uint4 pk;
+                                pk.x = pack_bf16x2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1]));
+                                pk.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                                pk.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                                pk.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                                *reinterpret_cast<uint4 *>(ob + lane * 64 + ((j ^ swz64) << 4)) = pk;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                *reinterpret_cast<float4 *>(ob + lane * 128 + ((j ^ swz) << 4)) =
+                                    make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        }
                         fence_proxy_async();
                         __syncwarp();
                         if (lane == 0) {
@@ -483,7 +508,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             tma_store_commit();
                         }
                         ++stores;
-                    } else if (row_ok) {
+                    } else if (row_ok && !OUT16) {       // (bf16 output always takes the TMA path; checked on the host)
                         if (p.vec_ok && col0 + 32 <= p.N) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4)
@@ -543,52 +568,59 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-// 2-D fp32 row-major [rows, cols] with row pitch ld (elements); box = [box_rows, 32 columns (128 B)], SWIZZLE_128B
-static int make_tmap_f32(CUtensorMap *tm, const float *ptr, int rows, int cols, int ld, int box_rows) {
+// 2-D row-major [rows, cols] tensor of fp32 (dt 0) or bf16 (dt 2) with row pitch ld (elements); box = [box_rows,
+// box_cols].  Operand tiles: 128-byte rows (32 fp32 / 64 bf16 columns), SWIZZLE_128B.  Epilogue tiles: 32 columns,
+// SWIZZLE_128B for fp32 (128-B rows) / SWIZZLE_64B for bf16 (64-B rows).
+static int make_tmap_2d(CUtensorMap *tm, int dt, const void *ptr, int rows, int cols, int ld, int box_rows, int box_cols) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled entry point not available");
         return VNEXT_ECUDA;
     }
+    const int esz = dt == VNEXT_BF16 ? 2 : 4;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(tm, dt == VNEXT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                     const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     box_cols * esz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed (%d) for [%d x %d] ld %d", (int)r, rows, cols, ld);
+        set_error("cuTensorMapEncodeTiled failed (%d) for [%d x %d] ld %d dtype %d", (int)r, rows, cols, ld, dt);
         return VNEXT_ECUDA;
     }
     return VNEXT_OK;
 }
 
-// 4-D fp32 NHWC tensor [T, H, W, C]; box = [1, box_h, box_w, 32 channels], SWIZZLE_128B
-static int make_tmap_nhwc(CUtensorMap *tm, const float *ptr, int T, int H, int W, int C, int box_h, int box_w) {
+// 4-D NHWC tensor [T, H, W, C]; box = [1, box_h, box_w, box_c channels]
+static int make_tmap_nhwc(CUtensorMap *tm, int dt, const void *ptr, int T, int H, int W, int C, int box_h, int box_w,
+                          int box_c) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled entry point not available");
         return VNEXT_ECUDA;
     }
+    const cuuint64_t esz = dt == VNEXT_BF16 ? 2 : 4;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T};
-    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-    cuuint32_t box[4] = {32u, (cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
+    cuuint64_t strides[3] = {(cuuint64_t)C * esz, (cuuint64_t)W * C * esz, (cuuint64_t)H * W * C * esz};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
     cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(tm, dt == VNEXT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                     const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     box_c * esz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled (NHWC) failed (%d) for [%d,%d,%d,%d]", (int)r, T, H, W, C);
+        set_error("cuTensorMapEncodeTiled (NHWC) failed (%d) for [%d,%d,%d,%d] dtype %d", (int)r, T, H, W, C, dt);
         return VNEXT_ECUDA;
     }
     return VNEXT_OK;
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int KIND, bool OUT16>
 static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &to, const CUtensorMap &tr,
                        GemmParams p, cudaStream_t stream) {
-    auto kern = gemm_tf32_kernel<BLOCK_N, STAGES>;
+    auto kern = gemm_tc_kernel<BLOCK_N, STAGES, KIND, OUT16>;
     constexpr size_t smem = (size_t)STAGES * (BLOCK_M * 128 + BLOCK_N * 128) + kEpiWarps * 8192 + 1024;
     static bool configured = false;
     if (!configured) {
@@ -622,31 +654,49 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUten
     return VNEXT_OK;
 }
 
+// operand format x output format -> instantiation
+static int launch_any(bool wide, int in_dt, int out_dt, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &to,
+                      const CUtensorMap &tr, const GemmParams &p, cudaStream_t stream) {
+    if (in_dt == VNEXT_F32 && out_dt == VNEXT_F32)
+        return wide ? launch_gemm<256, 3, 0, false>(ta, tb, to, tr, p, stream) : launch_gemm<128, 4, 0, false>(ta, tb, to, tr, p, stream);
+    if (in_dt == VNEXT_F32 && out_dt == VNEXT_BF16)
+        return wide ? launch_gemm<256, 3, 0, true>(ta, tb, to, tr, p, stream) : launch_gemm<128, 4, 0, true>(ta, tb, to, tr, p, stream);
+    if (in_dt == VNEXT_BF16 && out_dt == VNEXT_F32)
+        return wide ? launch_gemm<256, 3, 1, false>(ta, tb, to, tr, p, stream) : launch_gemm<128, 4, 1, false>(ta, tb, to, tr, p, stream);
+    if (in_dt == VNEXT_BF16 && out_dt == VNEXT_BF16)
+        return wide ? launch_gemm<256, 3, 1, true>(ta, tb, to, tr, p, stream) : launch_gemm<128, 4, 1, true>(ta, tb, to, tr, p, stream);
+    set_error("vnext_linear: unsupported dtypes (in %d, out %d)", in_dt, out_dt);
+    return VNEXT_EINVAL;
+}
+
 struct LinearArgs {
-    const float *a; int lda;
-    const float *w;
+    int in_dt, out_dt;       // VNEXT_F32 / VNEXT_BF16: a + weight, out + residual
+    const void *a; int lda;
+    const void *w;
     const float *bias;
     const float *bias2d; int period, ldb2;
     const unsigned char *row_mask; int mask_cols;
-    const float *residual; int ldr;
+    const void *residual; int ldr;
     const float *gamma, *beta; float eps;
-    float *out; int ldo;
+    void *out; int ldo;
     int M, N, K, flags;
 };
 
 static inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-int linear_tf32_device(const LinearArgs &x, cudaStream_t stream) {
+int linear_tc_device(const LinearArgs &x, cudaStream_t stream) {
     if (x.M == 0 || x.N == 0) return VNEXT_OK;
+    const int oe = x.out_dt == VNEXT_BF16 ? 8 : 4;           // elements per 16 bytes of out / residual
     GemmParams p;
     p.M = x.M; p.N = x.N; p.K = x.K; p.bias = x.bias; p.bias2d = x.bias2d; p.period = x.period > 0 ? x.period : 1;
-    p.ldb2 = x.ldb2; p.row_mask = x.row_mask; p.mask_cols = x.mask_cols; p.residual = x.residual; p.gamma = x.gamma;
-    p.beta = x.beta; p.out = x.out; p.ldo = x.ldo; p.ldr = x.ldr; p.flags = x.flags; p.eps = x.eps;
+    p.ldb2 = x.ldb2; p.row_mask = x.row_mask; p.mask_cols = x.mask_cols; p.residual = static_cast<const float *>(x.residual);
+    p.gamma = x.gamma; p.beta = x.beta; p.out = static_cast<float *>(x.out); p.ldo = x.ldo; p.ldr = x.ldr; p.flags = x.flags;
+    p.eps = x.eps;
     p.num_m_tiles = p.num_n_tiles = 0;
     p.conv = p.conv_cin_blocks = p.conv_tiles_x = p.conv_tiles_y = 0;
     p.cluster = 1;
-    p.vec_ok = al16(x.out) && x.ldo % 4 == 0 && (!x.bias || al16(x.bias)) &&
-               (!x.bias2d || (al16(x.bias2d) && x.ldb2 % 4 == 0)) && (!x.residual || (al16(x.residual) && x.ldr % 4 == 0));
+    p.vec_ok = al16(x.out) && x.ldo % oe == 0 && (!x.bias || al16(x.bias)) &&
+               (!x.bias2d || (al16(x.bias2d) && x.ldb2 % 4 == 0)) && (!x.residual || (al16(x.residual) && x.ldr % oe == 0));
     // 256-wide tiles only when N is a multiple of 256.  Measured (720p encoder offsets|logits projection, N = 384):
     // 256 + half-empty 256 tiles take 103 us per call against 84 us for three 128-wide tiles, so partial wide tiles lose.
     const bool wide = (x.N % 256 == 0);
@@ -656,8 +706,9 @@ int linear_tf32_device(const LinearArgs &x, cudaStream_t stream) {
             return VNEXT_EINVAL;
         }
     }
+    const int kbox = x.in_dt == VNEXT_BF16 ? 64 : 32;
     CUtensorMap ta, tb, to, tr;
-    int rc = make_tmap_f32(&ta, x.a, x.M, x.K, x.lda, BLOCK_M);
+    int rc = make_tmap_2d(&ta, x.in_dt, x.a, x.M, x.K, x.lda, BLOCK_M, kbox);
     if (rc) return rc;
     {   // pair CTAs (weight-tile multicast) whenever there are enough m-tiles to keep every SM busy in pairs
         static const char *env = getenv("VNEXT_GEMM_CLUSTER");
@@ -665,31 +716,36 @@ int linear_tf32_device(const LinearArgs &x, cudaStream_t stream) {
         const int m_tiles = (x.M + BLOCK_M - 1) / BLOCK_M;
         if (want == 2 && m_tiles * ((x.N + (wide ? 255 : 127)) / (wide ? 256 : 128)) >= 2 * num_sms()) p.cluster = 2;
     }
-    rc = make_tmap_f32(&tb, x.w, x.N, x.K, x.K, (wide ? 256 : 128) / p.cluster);
+    rc = make_tmap_2d(&tb, x.in_dt, x.w, x.N, x.K, x.K, (wide ? 256 : 128) / p.cluster, kbox);
     if (rc) return rc;
     // coalesced epilogue through shared memory + TMA needs 16-byte aligned rows of out (and residual)
-    p.tma_epi = al16(x.out) && x.ldo % 4 == 0 && (!x.residual || (al16(x.residual) && x.ldr % 4 == 0));
-    if (x.flags & 0x400) p.tma_epi = 0;                              // debug: force the direct-store epilogue
+    p.tma_epi = al16(x.out) && x.ldo % oe == 0 && (!x.residual || (al16(x.residual) && x.ldr % oe == 0));
+    if ((x.flags & 0x400) && x.out_dt == VNEXT_F32) p.tma_epi = 0;   // debug: force the direct-store epilogue
+    if (x.out_dt == VNEXT_BF16 && !p.tma_epi) {
+        set_error("vnext_linear: bf16 output / residual rows must be 16-byte aligned (ldo %d, ldr %d)", x.ldo, x.ldr);
+        return VNEXT_EINVAL;
+    }
     to = ta;
     tr = ta;
     if (p.tma_epi) {
-        rc = make_tmap_f32(&to, x.out, x.M, x.N, x.ldo, 32);
+        rc = make_tmap_2d(&to, x.out_dt, x.out, x.M, x.N, x.ldo, 32, 32);
         if (rc) return rc;
         if (x.residual) {
-            rc = make_tmap_f32(&tr, x.residual, x.M, x.N, x.ldr, 32);
+            rc = make_tmap_2d(&tr, x.out_dt, x.residual, x.M, x.N, x.ldr, 32, 32);
             if (rc) return rc;
         }
     }
-    return wide ? launch_gemm<256, 3>(ta, tb, to, tr, p, stream) : launch_gemm<128, 4>(ta, tb, to, tr, p, stream);
+    return launch_any(wide, x.in_dt, x.out_dt, ta, tb, to, tr, p, stream);
 }
 
-int conv3x3_tf32_device(const float *x, const float *w, const float *bias, float *out, int T, int H, int W, int Cin,
-                        int Cout, int relu, cudaStream_t stream) {
+int conv3x3_tc_device(int in_dt, int out_dt, const void *x, const void *w, const float *bias, void *out, int T, int H, int W,
+                      int Cin, int Cout, int relu, cudaStream_t stream) {
+    const int kbox = in_dt == VNEXT_BF16 ? 64 : 32;
     GemmParams p;
     p.M = T * H * W; p.N = Cout; p.K = 9 * Cin; p.bias = bias; p.bias2d = nullptr; p.period = 1; p.ldb2 = 0;
-    p.row_mask = nullptr; p.mask_cols = 0; p.residual = nullptr; p.gamma = p.beta = nullptr; p.out = out; p.ldo = Cout;
-    p.ldr = 0; p.flags = relu ? EPI_RELU : 0; p.eps = 0.f; p.vec_ok = 1; p.tma_epi = 1;
-    p.conv = 1; p.conv_cin_blocks = Cin / 32; p.conv_tiles_x = (W + 15) / 16; p.conv_tiles_y = (H + 7) / 8;
+    p.row_mask = nullptr; p.mask_cols = 0; p.residual = nullptr; p.gamma = p.beta = nullptr; p.out = static_cast<float *>(out);
+    p.ldo = Cout; p.ldr = 0; p.flags = relu ? EPI_RELU : 0; p.eps = 0.f; p.vec_ok = 1; p.tma_epi = 1;
+    p.conv = 1; p.conv_cin_blocks = Cin / kbox; p.conv_tiles_x = (W + 15) / 16; p.conv_tiles_y = (H + 7) / 8;
     p.num_m_tiles = T * p.conv_tiles_x * p.conv_tiles_y;
     p.num_n_tiles = 0;
     p.cluster = 1;
@@ -700,45 +756,75 @@ int conv3x3_tf32_device(const float *x, const float *w, const float *bias, float
         if (want == 2 && p.num_m_tiles * ((Cout + (wide ? 255 : 127)) / (wide ? 256 : 128)) >= 2 * num_sms()) p.cluster = 2;
     }
     CUtensorMap ta, tb, to;
-    int rc = make_tmap_nhwc(&ta, x, T, H, W, Cin, 8, 16);
+    int rc = make_tmap_nhwc(&ta, in_dt, x, T, H, W, Cin, 8, 16, kbox);
     if (rc) return rc;
-    rc = make_tmap_f32(&tb, w, Cout, 9 * Cin, 9 * Cin, (wide ? 256 : 128) / p.cluster);
+    rc = make_tmap_2d(&tb, in_dt, w, Cout, 9 * Cin, 9 * Cin, (wide ? 256 : 128) / p.cluster, kbox);
     if (rc) return rc;
-    rc = make_tmap_nhwc(&to, out, T, H, W, Cout, 2, 16);
+    rc = make_tmap_nhwc(&to, out_dt, out, T, H, W, Cout, 2, 16, 32);
     if (rc) return rc;
-    return wide ? launch_gemm<256, 3>(ta, tb, to, to, p, stream) : launch_gemm<128, 4>(ta, tb, to, to, p, stream);
+    return launch_any(wide, in_dt, out_dt, ta, tb, to, to, p, stream);
 }
 
 }  // namespace vnext
 
 using namespace vnext;
 
+static int conv3x3_checked(const char *who, int in_dt, int out_dt, const void *x, const void *w, const float *bias, void *out,
+                           int T, int H, int W, int Cin, int Cout, int relu, void *stream) {
+    VNEXT_CHECK_ARG((in_dt == VNEXT_F32 || in_dt == VNEXT_BF16) && (out_dt == VNEXT_F32 || out_dt == VNEXT_BF16),
+                    "%s: dtypes must be fp32 (0) or bf16 (2)", who);
+    VNEXT_CHECK_ARG(T >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "%s: bad shape", who);
+    const int kb = in_dt == VNEXT_BF16 ? 64 : 32, oa = out_dt == VNEXT_BF16 ? 8 : 4;
+    VNEXT_CHECK_ARG(Cin % kb == 0 && Cout % oa == 0, "%s: needs Cin %% %d == 0 and Cout %% %d == 0 (got %d, %d)", who, kb, oa, Cin, Cout);
+    if (T == 0) return VNEXT_OK;
+    VNEXT_CHECK_ARG(x && w && out && al16(x) && al16(w) && al16(out) && (!bias || al16(bias)), "%s: null or unaligned pointer", who);
+    VNEXT_CHECK_ARG((long long)T * H * W < (1ll << 31), "%s: too many pixels", who);
+    return conv3x3_tc_device(in_dt, out_dt, x, w, bias, out, T, H, W, Cin, Cout, relu, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int vnext_conv3x3_tf32(const float *x, const float *weight_khwc, const float *bias, float *out, int T, int H,
                                   int W, int Cin, int Cout, int relu, void *stream) {
-    VNEXT_CHECK_ARG(T >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "vnext_conv3x3_tf32: bad shape");
-    VNEXT_CHECK_ARG(Cin % 32 == 0 && Cout % 4 == 0, "vnext_conv3x3_tf32: needs Cin %% 32 == 0 and Cout %% 4 == 0 (got %d, %d)",
-                    Cin, Cout);
-    if (T == 0) return VNEXT_OK;
-    VNEXT_CHECK_ARG(x && weight_khwc && out && al16(x) && al16(weight_khwc) && al16(out) && (!bias || al16(bias)),
-                    "vnext_conv3x3_tf32: null or unaligned pointer");
-    VNEXT_CHECK_ARG((long long)T * H * W < (1ll << 31), "vnext_conv3x3_tf32: too many pixels");
-    return conv3x3_tf32_device(x, weight_khwc, bias, out, T, H, W, Cin, Cout, relu, static_cast<cudaStream_t>(stream));
+    return conv3x3_checked("vnext_conv3x3_tf32", VNEXT_F32, VNEXT_F32, x, weight_khwc, bias, out, T, H, W, Cin, Cout, relu, stream);
+}
+
+extern "C" int vnext_conv3x3_tc(int in_dtype, int out_dtype, const void *x, const void *weight_khwc, const float *bias,
+                                void *out, int T, int H, int W, int Cin, int Cout, int relu, void *stream) {
+    return conv3x3_checked("vnext_conv3x3_tc", in_dtype, out_dtype, x, weight_khwc, bias, out, T, H, W, Cin, Cout, relu, stream);
+}
+
+static int linear_checked(const char *who, int in_dt, int out_dt, const void *a, int lda, const void *weight, const float *bias,
+                          const float *bias2d, int bias_period, int ldb2, const unsigned char *row_mask, int mask_cols,
+                          const void *residual, int ldr, const float *ln_gamma, const float *ln_beta, float ln_eps, void *out,
+                          int ldo, int M, int N, int K, int flags, void *stream) {
+    VNEXT_CHECK_ARG((in_dt == VNEXT_F32 || in_dt == VNEXT_BF16) && (out_dt == VNEXT_F32 || out_dt == VNEXT_BF16),
+                    "%s: dtypes must be fp32 (0) or bf16 (2)", who);
+    VNEXT_CHECK_ARG(M >= 0 && N >= 0 && K > 0, "%s: bad sizes M=%d N=%d K=%d", who, M, N, K);
+    VNEXT_CHECK_ARG(flags >= 0 && flags < 0x800 && !(flags & 0x0f0), "%s: unknown epilogue flags %d", who, flags);
+    if (M == 0 || N == 0) return VNEXT_OK;
+    VNEXT_CHECK_ARG(a && weight && out, "%s: null pointer", who);
+    const int ie = in_dt == VNEXT_BF16 ? 8 : 4;
+    VNEXT_CHECK_ARG(al16(a) && al16(weight) && lda % ie == 0 && K % ie == 0,
+                    "%s: a / weight must be 16-byte aligned with lda and K multiples of %d (TMA)", who, ie);
+    VNEXT_CHECK_ARG(!(flags & EPI_RESIDUAL) || residual, "%s: residual flag without residual pointer", who);
+    VNEXT_CHECK_ARG(!bias2d || bias_period > 0, "%s: bias2d needs a positive period", who);
+    VNEXT_CHECK_ARG(!row_mask || bias_period > 0, "%s: row_mask needs a positive period", who);
+    LinearArgs x{in_dt, out_dt, a, lda, weight, bias, bias2d, bias_period, ldb2, row_mask, mask_cols, residual, ldr,
+                 ln_gamma, ln_beta, ln_eps, out, ldo, M, N, K, flags};
+    return linear_tc_device(x, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vnext_linear_tf32(const float *a, int lda, const float *weight, const float *bias, const float *bias2d,
                                  int bias_period, int ldb2, const unsigned char *row_mask, int mask_cols,
                                  const float *residual, int ldr, const float *ln_gamma, const float *ln_beta,
                                  float ln_eps, float *out, int ldo, int M, int N, int K, int flags, void *stream) {
-    VNEXT_CHECK_ARG(M >= 0 && N >= 0 && K > 0, "vnext_linear_tf32: bad sizes M=%d N=%d K=%d", M, N, K);
-    VNEXT_CHECK_ARG(flags >= 0 && flags < 0x800 && !(flags & 0x0f0), "vnext_linear_tf32: unknown epilogue flags %d", flags);
-    if (M == 0 || N == 0) return VNEXT_OK;
-    VNEXT_CHECK_ARG(a && weight && out, "vnext_linear_tf32: null pointer");
-    VNEXT_CHECK_ARG(al16(a) && al16(weight) && lda % 4 == 0 && K % 4 == 0,
-                    "vnext_linear_tf32: a / weight must be 16-byte aligned with lda and K multiples of 4 (TMA)");
-    VNEXT_CHECK_ARG(!(flags & EPI_RESIDUAL) || residual, "vnext_linear_tf32: residual flag without residual pointer");
-    VNEXT_CHECK_ARG(!bias2d || bias_period > 0, "vnext_linear_tf32: bias2d needs a positive period");
-    VNEXT_CHECK_ARG(!row_mask || bias_period > 0, "vnext_linear_tf32: row_mask needs a positive period");
-    LinearArgs x{a, lda, weight, bias, bias2d, bias_period, ldb2, row_mask, mask_cols, residual, ldr,
-                 ln_gamma, ln_beta, ln_eps, out, ldo, M, N, K, flags};
-    return linear_tf32_device(x, static_cast<cudaStream_t>(stream));
+    return linear_checked("vnext_linear_tf32", VNEXT_F32, VNEXT_F32, a, lda, weight, bias, bias2d, bias_period, ldb2, row_mask,
+                          mask_cols, residual, ldr, ln_gamma, ln_beta, ln_eps, out, ldo, M, N, K, flags, stream);
+}
+
+extern "C" int vnext_linear_tc(int in_dtype, int out_dtype, const void *a, int lda, const void *weight, const float *bias,
+                               const float *bias2d, int bias_period, int ldb2, const unsigned char *row_mask, int mask_cols,
+                               const void *residual, int ldr, const float *ln_gamma, const float *ln_beta, float ln_eps,
+                               void *out, int ldo, int M, int N, int K, int flags, void *stream) {
+    return linear_checked("vnext_linear_tc", in_dtype, out_dtype, a, lda, weight, bias, bias2d, bias_period, ldb2, row_mask,
+                          mask_cols, residual, ldr, ln_gamma, ln_beta, ln_eps, out, ldo, M, N, K, flags, stream);
 }

@@ -24,7 +24,9 @@
 //     does not fit the shared-memory budget for this tile class (fine levels under coarse queries), take the global
 //     path inside the same loop: same arithmetic, corner rows read with LDG and explicit border predicates — exact
 //     for ANY sampling locations, the window is only a cache;
-//   * two CTAs per SM, one window buffer each: one CTA's TMA fill overlaps the other CTA's gather.
+//   * one persistent CTA of 16 warps per SM with TWO window buffers: the TMA fill of unit i+1 and the global loads of
+//     its sampling inputs (kept in registers) fly during the gather of unit i (a first version with two independent
+//     8-warp CTAs and no prefetch was latency-bound: 558 us vs 385 us for the tile kernel at 720p, see profiles/).
 // Host side needs the level shapes on the HOST (the TMA descriptors are built per call from them): the entry point
 // takes host copies of spatial_shapes / level_start_index (the Python layer caches them per shapes tensor).
 #include <cuda.h>
@@ -34,8 +36,9 @@
 namespace vnext {
 
 constexpr int kWinMaxL = 4;
-constexpr int kWinWarps = 8;
+constexpr int kWinWarps = 16;
 constexpr int kWinThreads = kWinWarps * 32;
+constexpr int kWinMaxPass = 4;               // 32-sample passes per warp per unit: a unit has <= 16 * 4 * 32 samples
 constexpr int kWinZeroBytes = 256;           // zero rows at the start of dynamic smem (target of skipped samples)
 constexpr uint32_t kWinGlobalFlag = 1u << 31;
 
@@ -65,6 +68,7 @@ struct WinParams {
     long long ref_batch_stride;
     void *out;
     int N, S, M, L, K, margin, total_units;
+    int buf_bytes;                           // size of one window buffer (two of them follow the zero rows)
 };
 
 __device__ __forceinline__ void tma_load_box4(uint32_t smem_dst, const CUtensorMap *tmap, int c0, int c1, int c2, int c3,
@@ -127,16 +131,42 @@ __device__ __forceinline__ float win_transpose_reduce(float (&a)[VEC], int lane)
     return a[0];
 }
 
+struct WinUnit {
+    int lq, m, n, qy0, qx0;
+};
+__device__ __forceinline__ WinUnit win_decode(const WinParams &p, int u) {
+    WinUnit w;
+    w.lq = 0;
+    while (w.lq + 1 < p.L && u >= p.cls[w.lq + 1].unit_begin) ++w.lq;
+    const WinClass &c = p.cls[w.lq];
+    int r = u - c.unit_begin;
+    w.m = r % p.M;
+    r /= p.M;
+    const int tx = r % c.tiles_x;
+    r /= c.tiles_x;
+    const int ty = r % c.tiles_y;
+    w.n = r / c.tiles_y;
+    w.qy0 = ty * c.th;
+    w.qx0 = tx * c.tw;
+    return w;
+}
+
+// One sample's raw front-end inputs, fetched one unit ahead of their use (the loads of unit i+1 fly during the gather of
+// unit i): classic = (x, y, attention weight); fused = (offset x, offset y, logit) + reference point (x, y).
+struct WinSampleIn {
+    float a0, a1, a2, r0, r1;
+};
+
 template <typename VT, int LK, bool FUSED>
-__global__ void __launch_bounds__(kWinThreads, 2) msda_fwd_window_kernel(const __grid_constant__ WinParams p) {
+__global__ void __launch_bounds__(kWinThreads, 1) msda_fwd_window_kernel(const __grid_constant__ WinParams p) {
     using RW = WinRow<VT>;
     constexpr int VEC = RW::VEC, LPC = RW::LPC, NG = 32 / LPC, ROWB = RW::ROWB;
     constexpr int PPP = 32 / LK;          // (query, head) pairs per 32-sample warp pass
     constexpr int UPR = 32 / VEC;         // 16-byte units per (pixel, head) row
     static_assert(LK % NG == 0 && 32 % LK == 0, "unsupported L*K for the window kernel");
 
-    extern __shared__ __align__(128) unsigned char win_smem[];
-    __shared__ __align__(8) uint64_t bar;
+    extern __shared__ __align__(128) unsigned char win_smem[];   // [zero rows][window buffer 0][window buffer 1]
+    __shared__ __align__(8) uint64_t bar[2];
     __shared__ __align__(16) uint4 table[kWinWarps][32];   // {row offsets | flags, attn*hh, attn*lh, lw}
     __shared__ int2 gtab[kWinWarps][32];                   // global path: {unit offset of the top-left corner, row stride}
 
@@ -146,44 +176,94 @@ __global__ void __launch_bounds__(kWinThreads, 2) msda_fwd_window_kernel(const _
 
     if (tid < kWinZeroBytes / 4) reinterpret_cast<uint32_t *>(win_smem)[tid] = 0u;
     if (tid == 0) {
-        mbar_init(&bar, 1);
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
         fence_mbar_init();
     }
     __syncthreads();
 
-    const unsigned char *vbytes = reinterpret_cast<const unsigned char *>(p.value);
-    uint32_t phase = 0;                          // parity of the next window fill (advances only when a fill is issued)
-    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-        int lq = 0;
-        while (lq + 1 < p.L && u >= p.cls[lq + 1].unit_begin) ++lq;
-        const WinClass &c = p.cls[lq];
-        int r = u - c.unit_begin;
-        const int m = r % p.M;
-        r /= p.M;
-        const int tx = r % c.tiles_x;
-        r /= c.tiles_x;
-        const int ty = r % c.tiles_y;
-        const int n = r / c.tiles_y;
-        const int qy0 = ty * c.th, qx0 = tx * c.tw;
-        // window origin of every sampled level: floor(centre of the tile's first query, in that level's pixels) - margin
+    // window fill of unit u into buffer b (one thread); returns nothing — whether a fill exists is recomputed by everyone
+    auto issue = [&](int u, int b) {
+        const WinUnit w = win_decode(p, u);
+        const WinClass &c = p.cls[w.lq];
         uint32_t tx_bytes = 0;
 #pragma unroll
         for (int l = 0; l < kWinMaxL; ++l)
             if (l < p.L && c.lv[l].staged) tx_bytes += (uint32_t)c.lv[l].bytes;
-        if (tid == 0 && tx_bytes) {
-            fence_proxy_async();
-            mbar_expect_tx(&bar, tx_bytes);
+        if (!tx_bytes) return;
+        fence_proxy_async();
+        mbar_expect_tx(&bar[b], tx_bytes);
+        const uint32_t base = smem_base + kWinZeroBytes + (uint32_t)b * (uint32_t)p.buf_bytes;
 #pragma unroll
-            for (int l = 0; l < kWinMaxL; ++l)
-                if (l < p.L && c.lv[l].staged)
-                    tma_load_box4(smem_base + c.lv[l].smem_off, &p.tmap[lq * kWinMaxL + l], m * 32,
-                                  floordiv((2 * qx0 + 1) * p.meta[l].W - c.W, 2 * c.W) - p.margin,
-                                  floordiv((2 * qy0 + 1) * p.meta[l].H - c.H, 2 * c.H) - p.margin, n, &bar);
+        for (int l = 0; l < kWinMaxL; ++l)
+            if (l < p.L && c.lv[l].staged)
+                tma_load_box4(base + c.lv[l].smem_off, &p.tmap[w.lq * kWinMaxL + l], w.m * 32,
+                              floordiv((2 * w.qx0 + 1) * p.meta[l].W - c.W, 2 * c.W) - p.margin,
+                              floordiv((2 * w.qy0 + 1) * p.meta[l].H - c.H, 2 * c.H) - p.margin, w.n, &bar[b]);
+    };
+    // raw inputs of this lane's samples in unit u (pass = warp + pi * kWinWarps)
+    auto prefetch = [&](int u, WinSampleIn (&in)[kWinMaxPass]) {
+        const WinUnit w = win_decode(p, u);
+        const WinClass &c = p.cls[w.lq];
+        const int nq = c.th * c.tw;
+#pragma unroll
+        for (int pi = 0; pi < kWinMaxPass; ++pi) {
+            const int idx = (warp + pi * kWinWarps) * 32 + lane;
+            const int qi = idx / LK, smp = idx % LK;
+            const int qr = qi / c.tw, qc = qi - qr * c.tw;
+            const int qy = w.qy0 + qr, qx = w.qx0 + qc;
+            in[pi].a0 = in[pi].a1 = in[pi].a2 = in[pi].r0 = in[pi].r1 = 0.f;
+            if (qi < nq && qy < c.H && qx < c.W) {
+                const int q = c.start + qy * c.W + qx;
+                const long long row = (long long)w.n * p.S + q;
+                if (FUSED) {
+                    const float *rowp = p.oa + row * p.oa_pitch;
+                    const float2 off = __ldg(reinterpret_cast<const float2 *>(rowp + (w.m * LK + smp) * 2));
+                    in[pi].a0 = off.x; in[pi].a1 = off.y;
+                    in[pi].a2 = __ldg(rowp + p.n_off + w.m * LK + smp);
+                    const float2 rf = __ldg(reinterpret_cast<const float2 *>(
+                        p.ref + w.n * p.ref_batch_stride + ((size_t)q * p.L + smp / p.K) * 2));
+                    in[pi].r0 = rf.x; in[pi].r1 = rf.y;
+                } else {
+                    const long long si = (row * p.M + w.m) * LK + smp;
+                    const float2 xy = __ldg(reinterpret_cast<const float2 *>(p.loc) + si);
+                    in[pi].a0 = xy.x; in[pi].a1 = xy.y;
+                    in[pi].a2 = __ldg(p.attn + si);
+                }
+            }
         }
+    };
+
+    const unsigned char *vbytes = reinterpret_cast<const unsigned char *>(p.value);
+    WinSampleIn cur[kWinMaxPass], nxt[kWinMaxPass];
+    int u = blockIdx.x;
+    if (u < p.total_units) {
+        if (tid == 0) issue(u, 0);
+        prefetch(u, cur);
+    }
+    uint32_t phase0 = 0, phase1 = 0;             // parity of the next fill of each buffer
+    for (int it = 0; u < p.total_units; u += gridDim.x, ++it) {
+        const int b = it & 1;
+        const int un = u + gridDim.x;
+        if (un < p.total_units) {                // buffer b^1 was released by the barrier that ended unit it-1
+            if (tid == 0) issue(un, b ^ 1);
+            prefetch(un, nxt);
+        }
+        const WinUnit w = win_decode(p, u);
+        const WinClass &c = p.cls[w.lq];
+        const int m = w.m, n = w.n, qy0 = w.qy0, qx0 = w.qx0;
+        bool filled = false;
+#pragma unroll
+        for (int l = 0; l < kWinMaxL; ++l)
+            if (l < p.L && c.lv[l].staged) filled = true;
+        const uint32_t buf_off = kWinZeroBytes + (uint32_t)b * (uint32_t)p.buf_bytes;
         const int nq = c.th * c.tw;
         const int npass = (nq * LK + 31) / 32;
-        bool waited = (tx_bytes == 0);
-        for (int pass = warp; pass < npass; pass += kWinWarps) {
+        bool waited = !filled;
+#pragma unroll
+        for (int pi = 0; pi < kWinMaxPass; ++pi) {
+            const int pass = warp + pi * kWinWarps;
+            if (pass >= npass) break;
             // ---- phase 1: one sample per lane
             const int idx = pass * 32 + lane;
             const int qi = idx / LK, smp = idx % LK;
@@ -192,32 +272,10 @@ __global__ void __launch_bounds__(kWinThreads, 2) msda_fwd_window_kernel(const _
             const bool live = qi < nq && qy < c.H && qx < c.W;
             const int lvl = smp / p.K;
             const LevelMeta lm = p.meta[lvl];
-            float x = 0.f, y = 0.f, a = 0.f;
-            const int q = c.start + qy * c.W + qx;                 // query index inside the batch element
-            const long long row = (long long)n * p.S + q;           // Lq == S
-            if (live) {
-                if (FUSED) {
-                    const float *rowp = p.oa + row * p.oa_pitch;
-                    const float2 off = __ldg(reinterpret_cast<const float2 *>(rowp + (m * LK + smp) * 2));
-                    a = __ldg(rowp + p.n_off + m * LK + smp);
-                    const float *rp = p.ref + n * p.ref_batch_stride + ((size_t)q * p.L + lvl) * p.ref_dim;
-                    if (p.ref_dim == 2) {
-                        const float2 rf = __ldg(reinterpret_cast<const float2 *>(rp));
-                        x = rf.x + off.x / (float)lm.W;
-                        y = rf.y + off.y / (float)lm.H;
-                    } else {
-                        const float4 rf = __ldg(reinterpret_cast<const float4 *>(rp));
-                        x = rf.x + off.x / (float)p.K * rf.z * 0.5f;
-                        y = rf.y + off.y / (float)p.K * rf.w * 0.5f;
-                    }
-                } else {
-                    const long long si = (row * p.M + m) * LK + smp;
-                    const float2 xy = __ldg(reinterpret_cast<const float2 *>(p.loc) + si);
-                    x = xy.x; y = xy.y;
-                    a = __ldg(p.attn + si);
-                }
-            }
+            float x, y, a = cur[pi].a2;
             if (FUSED) {
+                x = cur[pi].r0 + cur[pi].a0 / (float)lm.W;       // ref + offset / (W_l, H_l)   (module :102-105)
+                y = cur[pi].r1 + cur[pi].a1 / (float)lm.H;
                 float mx = live ? a : -INFINITY;
 #pragma unroll
                 for (int o = LK / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -226,24 +284,28 @@ __global__ void __launch_bounds__(kWinThreads, 2) msda_fwd_window_kernel(const _
 #pragma unroll
                 for (int o = LK / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
                 a = live ? e / sum : 0.f;
+            } else {
+                x = cur[pi].a0;
+                y = cur[pi].a1;
             }
             {
                 const float h_im = __fsub_rn(__fmul_rn(y, (float)lm.H), 0.5f);
                 const float w_im = __fsub_rn(__fmul_rn(x, (float)lm.W), 0.5f);
                 const bool inside = live && (h_im > -1.f) && (w_im > -1.f) && (h_im < (float)lm.H) && (w_im < (float)lm.W);
                 const float hf = floorf(h_im), wf = floorf(w_im);
-                const int h_low = (int)hf, w_low = (int)wf;
-                const float lh = h_im - hf, lw = w_im - wf;
                 uint32_t packed = 0u;                                 // both rows -> the zero region
-                float ahh = 0.f, alh = 0.f;
+                float ahh = 0.f, alh = 0.f, lw = 0.f;                 // skipped samples: all-zero weights (no NaN leaks)
                 if (inside) {
+                    const int h_low = (int)hf, w_low = (int)wf;
+                    const float lh = h_im - hf;
+                    lw = w_im - wf;
                     ahh = a * (1.f - lh);
                     alh = a * lh;
                     const WinLevelCfg cfg = c.lv[lvl];
                     const int rx = w_low - (floordiv((2 * qx0 + 1) * lm.W - c.W, 2 * c.W) - p.margin);
                     const int ry = h_low - (floordiv((2 * qy0 + 1) * lm.H - c.H, 2 * c.H) - p.margin);
                     if (cfg.staged && rx >= 0 && rx + 1 < cfg.bw && ry >= 0 && ry + 1 < cfg.bh) {
-                        const uint32_t off0 = (uint32_t)(cfg.smem_off + ry * cfg.pitch + rx * ROWB);
+                        const uint32_t off0 = buf_off + (uint32_t)(cfg.smem_off + ry * cfg.pitch + rx * ROWB);
                         packed = (off0 >> 4) | (((off0 + (uint32_t)cfg.pitch) >> 4) << 14);
                     } else {
                         const uint32_t v = (h_low >= 0 ? 1u : 0u) | (h_low + 1 <= lm.H - 1 ? 2u : 0u) |
@@ -257,7 +319,7 @@ __global__ void __launch_bounds__(kWinThreads, 2) msda_fwd_window_kernel(const _
             }
             __syncwarp();
             if (!waited) {
-                mbar_wait(&bar, phase);
+                mbar_wait(&bar[b], b ? phase1 : phase0);
                 waited = true;
             }
             // ---- phase 2: one lane group per sample, four corner rows per sample
@@ -284,12 +346,12 @@ __global__ void __launch_bounds__(kWinThreads, 2) msda_fwd_window_kernel(const _
                     } else {
                         const int2 g = gtab[warp][s];
                         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-                        const uint4 *b = reinterpret_cast<const uint4 *>(vbytes + (long long)g.x * 16) + sub;
+                        const uint4 *bp = reinterpret_cast<const uint4 *>(vbytes + (long long)g.x * 16) + sub;
                         const bool h0 = e.x & 1u, h1 = e.x & 2u, w0 = e.x & 4u, w1 = e.x & 8u;
-                        t00 = (h0 && w0) ? __ldg(b) : z;
-                        t01 = (h0 && w1) ? __ldg(b + p.M * UPR) : z;
-                        t10 = (h1 && w0) ? __ldg(b + g.y) : z;
-                        t11 = (h1 && w1) ? __ldg(b + g.y + p.M * UPR) : z;
+                        t00 = (h0 && w0) ? __ldg(bp) : z;
+                        t01 = (h0 && w1) ? __ldg(bp + p.M * UPR) : z;
+                        t10 = (h1 && w0) ? __ldg(bp + g.y) : z;
+                        t11 = (h1 && w1) ? __ldg(bp + g.y + p.M * UPR) : z;
                     }
                     float v[VEC];
                     RW::widen(t00, v);
@@ -316,9 +378,13 @@ __global__ void __launch_bounds__(kWinThreads, 2) msda_fwd_window_kernel(const _
             }
             __syncwarp();
         }
-        if (!waited) mbar_wait(&bar, phase);    // every thread observes every fill
-        if (tx_bytes) phase ^= 1u;
-        __syncthreads();                        // all gathers of this unit are done: the window may be overwritten
+        if (!waited) mbar_wait(&bar[b], b ? phase1 : phase0);   // every thread observes every fill
+        if (filled) {
+            if (b) phase1 ^= 1u; else phase0 ^= 1u;
+        }
+        __syncthreads();                        // all gathers of this unit are done: its buffer may be refilled
+#pragma unroll
+        for (int pi = 0; pi < kWinMaxPass; ++pi) cur[pi] = nxt[pi];
     }
 }
 
@@ -374,11 +440,12 @@ static bool plan_class(int lq, int L, int K, const int *H, const int *W, int row
     for (auto &tt : cand) {
         const int th = tt[0] < H[lq] ? tt[0] : H[lq], tw = tt[1] < W[lq] ? tt[1] : W[lq];
         const double nq = (double)th * tw;
+        if (th * tw * L * K > kWinWarps * kWinMaxPass * 32) continue;     // a unit's samples must fit the warps' passes
         // staging options: levels >= first (coarser or equal to `first`), first = 0 .. L (L = nothing staged)
         for (int first = 0; first <= L; ++first) {
             WinPlanChoice ch;
             ch.th = th; ch.tw = tw;
-            size_t off = kWinZeroBytes;
+            size_t off = 0;                        // offsets are relative to the window buffer
             double staged_bytes = 0.0, unstaged = 0.0;
             bool ok = true;
             for (int l = 0; l < L; ++l) {
@@ -397,9 +464,9 @@ static bool plan_class(int lq, int L, int K, const int *H, const int *W, int row
                 staged_bytes += cfg.bytes;
             }
             if (!ok || off > budget || off >= (1u << 18)) continue;
-            // per query: window bytes pulled from L2 + un-staged levels' corner rows (L2 gather, penalised 3x: latency-
-            // bound path) + a fixed per-unit cost (TMA round trip, barrier) worth ~16 KB of traffic
-            const double cost = (staged_bytes + 16384.0) / nq + unstaged * K * 4 * rowb * 3.0;
+            // per query: window bytes pulled from L2 + un-staged levels' corner rows (L2 gather, penalised 2x: latency-
+            // bound path) + a fixed per-unit cost (barriers, pipeline bubbles of small units) worth ~64 KB of traffic
+            const double cost = (staged_bytes + 65536.0) / nq + unstaged * K * 4 * rowb * 2.0;
             if (cost < best->cost) {
                 *best = ch;
                 best->cost = cost;
@@ -464,9 +531,9 @@ int msda_forward_window_device(int dtype, const void *value, const int64_t *hsha
     VNEXT_CHECK_ARG(margin >= 0 && margin <= 64, "msda window kernel: margin out of range");
     const bool fused = oa != nullptr;
     if (fused) {
-        VNEXT_CHECK_ARG(ref && (ref_dim == 2 || ref_dim == 4) && oa_pitch >= M * LK * 3 && oa_pitch % 2 == 0 &&
-                            (reinterpret_cast<uintptr_t>(oa) & 7u) == 0 && (reinterpret_cast<uintptr_t>(ref) & 15u) == 0,
-                        "msda window kernel: bad fused front-end arguments");
+        VNEXT_CHECK_ARG(ref && ref_dim == 2 && oa_pitch >= M * LK * 3 && oa_pitch % 2 == 0 &&
+                            (reinterpret_cast<uintptr_t>(oa) & 7u) == 0 && (reinterpret_cast<uintptr_t>(ref) & 7u) == 0,
+                        "msda window kernel: bad fused front-end arguments (2-d reference points only: encoder self-attention)");
     } else {
         VNEXT_CHECK_ARG(loc && attn && (reinterpret_cast<uintptr_t>(loc) & 7u) == 0, "msda window kernel: bad loc/attn pointers");
     }
@@ -487,8 +554,8 @@ int msda_forward_window_device(int dtype, const void *value, const int64_t *hsha
     WinParams p;
     memset(&p, 0, sizeof(p));
     const int esz = dtype == VNEXT_F32 ? 4 : 2, rowb = 32 * esz;
-    const size_t budget = 104 * 1024;
-    size_t smem = kWinZeroBytes;
+    const size_t budget = 106 * 1024;             // per window buffer; two buffers + zero rows + 12 KB static < 227 KB
+    size_t smem = 0;
     int units = 0;
     for (int lq = 0; lq < L; ++lq) {
         WinPlanChoice ch;
@@ -528,6 +595,8 @@ int msda_forward_window_device(int dtype, const void *value, const int64_t *hsha
     p.value = value; p.loc = loc; p.attn = attn; p.oa = oa; p.oa_pitch = oa_pitch; p.n_off = M * LK * 2;
     p.ref = ref; p.ref_dim = ref_dim; p.ref_batch_stride = ref_shared ? 0 : (long long)S * L * ref_dim;
     p.out = out; p.N = N; p.S = S; p.M = M; p.L = L; p.K = K; p.margin = margin; p.total_units = units;
+    p.buf_bytes = (int)((smem + 127) / 128 * 128);
+    smem = kWinZeroBytes + 2 * (size_t)p.buf_bytes;
     int rc;
     if (dtype == VNEXT_F32)
         rc = fused ? dispatch_window<float, true>(p, LK, smem, stream) : dispatch_window<float, false>(p, LK, smem, stream);

@@ -11,29 +11,33 @@ def _st(t):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+_DT = {torch.float32: _cabi.F32, torch.bfloat16: _cabi.BF16}
+
+
 def bias_act(x, bias, relu=True, residual=None, out=None):
     """x: [..., C] contiguous (NHWC); returns act(x + bias (+ residual)); in place when out is x."""
     C = x.shape[-1]
     assert x.is_contiguous() and (residual is None or residual.is_contiguous())
     out = torch.empty_like(x) if out is None else out
     rows = x.numel() // C
-    info = {"bytes": 4.0 * x.numel() * (3 if residual is not None else 2)}
-    rc = _cabi.timed_call("bias_act", info, x, lambda: _cabi.lib().vnext_bias_act(
-        x.data_ptr(), bias.data_ptr(), None if residual is None else residual.data_ptr(), out.data_ptr(), rows, C,
+    assert out.dtype == x.dtype and (residual is None or residual.dtype == x.dtype)
+    info = {"bytes": float(x.element_size()) * x.numel() * (3 if residual is not None else 2)}
+    rc = _cabi.timed_call("bias_act", info, x, lambda: _cabi.lib().vnext_bias_act_dt(
+        _DT[x.dtype], x.data_ptr(), bias.data_ptr(), None if residual is None else residual.data_ptr(), out.data_ptr(), rows, C,
         int(relu), _st(x)))
     _cabi.check(rc, "vnext_bias_act")
     return out
 
 
-def stem_pool(x, bias):
+def stem_pool(x, bias, out_dtype=None):
     """x: [N, H, W, C] conv output (NHWC contiguous) -> maxpool3x3s2p1(relu(x + bias)) [N, Ho, Wo, C]."""
     N, H, W, C = x.shape
     assert x.is_contiguous()
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
-    out = torch.empty((N, Ho, Wo, C), dtype=x.dtype, device=x.device)
-    info = {"bytes": 4.0 * (x.numel() + out.numel())}
-    rc = _cabi.timed_call("stem_pool", info, x, lambda: _cabi.lib().vnext_stem_pool(
-        x.data_ptr(), bias.data_ptr(), out.data_ptr(), N, H, W, C, _st(x)))
+    out = torch.empty((N, Ho, Wo, C), dtype=out_dtype or x.dtype, device=x.device)
+    info = {"bytes": float(x.element_size() * x.numel() + out.element_size() * out.numel())}
+    rc = _cabi.timed_call("stem_pool", info, x, lambda: _cabi.lib().vnext_stem_pool_dt(
+        _DT[x.dtype], _DT[out.dtype], x.data_ptr(), bias.data_ptr(), out.data_ptr(), N, H, W, C, _st(x)))
     _cabi.check(rc, "vnext_stem_pool")
     return out
 
@@ -47,25 +51,25 @@ def groupnorm_nhwc(x, gamma, beta, groups=32, eps=1e-5, out=None, stats_ws=None)
     assert out.stride(2) == 1 and out.stride(1) == C
     if stats_ws is None:
         stats_ws = torch.empty(_cabi.lib().vnext_groupnorm_workspace_floats(N, HW, groups), dtype=torch.float32, device=x.device)
-    info = {"bytes": 4.0 * x.numel() * 3}
-    rc = _cabi.timed_call("groupnorm_nhwc", info, x, lambda: _cabi.lib().vnext_groupnorm_nhwc(
-        x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), out.stride(0), stats_ws.data_ptr(), N, HW, C,
-        groups, float(eps), _st(x)))
+    info = {"bytes": float(x.element_size() * x.numel() * 2 + out.element_size() * x.numel())}
+    rc = _cabi.timed_call("groupnorm_nhwc", info, x, lambda: _cabi.lib().vnext_groupnorm_nhwc_dt(
+        _DT[x.dtype], _DT[out.dtype], x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), out.stride(0),
+        stats_ws.data_ptr(), N, HW, C, groups, float(eps), _st(x)))
     _cabi.check(rc, "vnext_groupnorm_nhwc")
     return out
 
 
-def preprocess(frames, mean, std, Hp, Wp, out=None):
-    """frames [T,3,H,W] uint8 or float32 on device -> normalised zero-padded NHWC [T,Hp,Wp,3]."""
+def preprocess(frames, mean, std, Hp, Wp, out=None, out_dtype=torch.float32):
+    """frames [T,3,H,W] uint8 or float32 on device -> normalised zero-padded NHWC [T,Hp,Wp,3] (fp32 or bf16)."""
     T, _, H, W = frames.shape
     assert frames.is_contiguous() and frames.dtype in (torch.uint8, torch.float32)
     if out is None:
-        out = torch.empty((T, Hp, Wp, 3), dtype=torch.float32, device=frames.device)
+        out = torch.empty((T, Hp, Wp, 3), dtype=out_dtype, device=frames.device)
     m = (ctypes.c_float * 3)(*[float(v) for v in mean])
     s = (ctypes.c_float * 3)(*[float(v) for v in std])
-    info = {"bytes": float(frames.numel() * frames.element_size() + out.numel() * 4)}
-    rc = _cabi.timed_call("preprocess", info, frames, lambda: _cabi.lib().vnext_preprocess(
-        int(frames.dtype == torch.uint8), frames.data_ptr(), out.data_ptr(), T, H, W, Hp, Wp,
+    info = {"bytes": float(frames.numel() * frames.element_size() + out.numel() * out.element_size())}
+    rc = _cabi.timed_call("preprocess", info, frames, lambda: _cabi.lib().vnext_preprocess_dt(
+        int(frames.dtype == torch.uint8), _DT[out.dtype], frames.data_ptr(), out.data_ptr(), T, H, W, Hp, Wp,
         ctypes.cast(m, ctypes.c_void_p), ctypes.cast(s, ctypes.c_void_p), _st(frames)))
     _cabi.check(rc, "vnext_preprocess")
     return out

@@ -45,7 +45,7 @@ class IDOLEngine(SeqFormerEngine):
             out = self._mha(q, out, w["self_attn"], residual=out, ln=w["norm2"])
             a = w["attn"]
             oa = self.lin(out + qpos, (a["oa_w"], a["oa_b"]))
-            s = self.sample(self._value(memory, a, plan), oa, ref_in, plan, a["n_off"])
+            s = self.sample(self._value(memory, a, plan), oa, ref_in, plan, a["n_off"]).float()
             out = self.lin(s, (a["o_w"], a["o_b"]), residual=out, ln=w["norm1"])
             out = self.lin(self.lin(out, w["linear1"], relu=True), w["linear2"], residual=out, ln=w["norm3"])
             tmp = self._mlp(out, w["bbox"])

@@ -21,16 +21,25 @@ def _rows(t, n):
     return t2 if t2.stride(-1) == 1 else t2.contiguous()
 
 
+_DT = {torch.float32: _cabi.F32, torch.bfloat16: _cabi.BF16}
+
+
 def linear(x, weight, bias=None, relu=False, gelu=False, residual=None, ln_weight=None, ln_bias=None, ln_eps=1e-5, out=None,
-           bias2d=None, row_mask=None, mask_cols=0, name=None, _debug_flags=0):
+           bias2d=None, row_mask=None, mask_cols=0, name=None, _debug_flags=0, out_dtype=None):
+    """x and weight share a dtype (fp32 -> TF32 MMAs, bf16 -> bf16 MMAs); out_dtype (default: x's) is also the dtype the
+    residual is read in; bias / bias2d / LayerNorm parameters are fp32."""
     if not x.is_cuda:
         raise RuntimeError("vnext_b200.linear: CUDA tensors only (no CPU fallback)")
     K = x.shape[-1]
     N = weight.shape[0]
     x2 = _rows(x, K)
     M = x2.shape[0]
+    if x.dtype != weight.dtype or x.dtype not in _DT:
+        raise RuntimeError(f"vnext_b200.linear: x ({x.dtype}) and weight ({weight.dtype}) must both be fp32 or both bf16")
     if out is None:
-        out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        out = torch.empty((M, N), dtype=out_dtype or x.dtype, device=x.device)
+    if residual is not None and residual.dtype != out.dtype:
+        residual = residual.to(out.dtype)
     out2 = out.view(-1, out.shape[-1])[:, :N] if out.shape[-1] != N else out.view(-1, N)
     flags = (EPI_RELU if relu else 0) | (EPI_GELU if gelu else 0) | _debug_flags
     res2 = None
@@ -44,30 +53,36 @@ def linear(x, weight, bias=None, relu=False, gelu=False, residual=None, ln_weigh
         period = bias2d.shape[0]
     elif row_mask is not None:
         period = row_mask.shape[0]
+    ie, oe = x.element_size(), out.element_size()
     info = {"flops": 2.0 * M * N * K,
-            "bytes": 4.0 * (M * K + N * K + M * N * (2 if residual is not None else 1) + (M * N if bias2d is not None else 0))}
+            "bytes": float(ie * (M * K + N * K) + oe * M * N * (2 if residual is not None else 1)
+                           + (4 * M * N if bias2d is not None else 0))}
+    tag = "tf32" if x.dtype == torch.float32 else "bf16"
     with torch.cuda.device(x.device):
         rc = _cabi.timed_call(
-            name or f"linear_tf32_n{N}_k{K}_f{flags}", info, x,
-            lambda: _cabi.lib().vnext_linear_tf32(
-                x2.data_ptr(), x2.stride(0), weight.data_ptr(), _ptr(bias), _ptr(bias2d), period,
+            name or f"linear_{tag}_n{N}_k{K}_f{flags}", info, x,
+            lambda: _cabi.lib().vnext_linear_tc(
+                _DT[x.dtype], _DT[out.dtype], x2.data_ptr(), x2.stride(0), weight.data_ptr(), _ptr(bias), _ptr(bias2d), period,
                 0 if bias2d is None else bias2d.stride(0), _ptr(row_mask), int(mask_cols), _ptr(res2),
                 0 if res2 is None else res2.stride(0), _ptr(ln_weight), _ptr(ln_bias), float(ln_eps), out2.data_ptr(),
                 out2.stride(0), M, N, K, flags, torch.cuda.current_stream(x.device).cuda_stream))
-    _cabi.check(rc, "vnext_linear_tf32")
+    _cabi.check(rc, "vnext_linear_tc")
     return out2.view(*x.shape[:-1], N) if out2.is_contiguous() else out2
 
 
-def conv3x3(x, weight_khwc, bias, relu=True):
-    """x [T,H,W,Cin] contiguous NHWC; weight_khwc [Cout, 9*Cin] (= conv weight.permute(0,2,3,1)); stride 1, padding 1."""
+def conv3x3(x, weight_khwc, bias, relu=True, out_dtype=None):
+    """x [T,H,W,Cin] contiguous NHWC; weight_khwc [Cout, 9*Cin] (= conv weight.permute(0,2,3,1)); stride 1, padding 1.
+    x / weight fp32 (TF32 MMAs) or bf16; output dtype defaults to x's."""
     T, H, W, Cin = x.shape
     Cout = weight_khwc.shape[0]
-    assert x.is_contiguous() and weight_khwc.is_contiguous()
-    out = torch.empty((T, H, W, Cout), dtype=torch.float32, device=x.device)
-    info = {"flops": 2.0 * T * H * W * Cout * 9 * Cin, "bytes": 4.0 * (x.numel() + out.numel() + weight_khwc.numel())}
+    assert x.is_contiguous() and weight_khwc.is_contiguous() and x.dtype == weight_khwc.dtype
+    out = torch.empty((T, H, W, Cout), dtype=out_dtype or x.dtype, device=x.device)
+    info = {"flops": 2.0 * T * H * W * Cout * 9 * Cin,
+            "bytes": float(x.element_size() * (x.numel() + weight_khwc.numel()) + out.element_size() * out.numel())}
+    tag = "tf32" if x.dtype == torch.float32 else "bf16"
     with torch.cuda.device(x.device):
-        rc = _cabi.timed_call(f"conv3x3_tf32_c{Cin}_n{Cout}", info, x, lambda: _cabi.lib().vnext_conv3x3_tf32(
-            x.data_ptr(), weight_khwc.data_ptr(), _ptr(bias), out.data_ptr(), T, H, W, Cin, Cout, int(relu),
-            torch.cuda.current_stream(x.device).cuda_stream))
-    _cabi.check(rc, "vnext_conv3x3_tf32")
+        rc = _cabi.timed_call(f"conv3x3_{tag}_c{Cin}_n{Cout}", info, x, lambda: _cabi.lib().vnext_conv3x3_tc(
+            _DT[x.dtype], _DT[out.dtype], x.data_ptr(), weight_khwc.data_ptr(), _ptr(bias), out.data_ptr(), T, H, W, Cin,
+            Cout, int(relu), torch.cuda.current_stream(x.device).cuda_stream))
+    _cabi.check(rc, "vnext_conv3x3_tc")
     return out

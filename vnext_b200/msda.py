@@ -55,6 +55,47 @@ def _check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_w
     return N, S, M, D, L, Lq, P
 
 
+# ---------------------------------------------------------------- self-attention (encoder shape) window kernel
+# "auto": use the shared-memory window kernel whenever the queries are the pixel grid (Lq == S) and the shape is
+# supported; "off": never.  The window kernel is exact for any sampling locations (out-of-window samples are read
+# from global memory), it is just slower than the tile kernel when the locations have no spatial locality.
+WINDOW_MODE = "auto"
+WINDOW_MARGIN = {torch.float32: 4, torch.bfloat16: 6}      # pixels around the tile footprint staged per level
+_HOST_SHAPES = {}
+
+
+def host_geometry(spatial_shapes, level_start_index):
+    """HOST copies (numpy int64) of the two geometry tensors, cached per tensor (one device sync per new tensor; the
+    engines pass their plan's host copies instead and never hit this)."""
+    key = (spatial_shapes.data_ptr(), spatial_shapes._version, level_start_index.data_ptr(), level_start_index._version,
+           spatial_shapes.device.index)
+    hit = _HOST_SHAPES.get(key)
+    if hit is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("ms_deform_attn: spatial_shapes must be known on the host before CUDA-graph capture "
+                               "(call msda.host_geometry(shapes, lsi) once outside the capture)")
+        if len(_HOST_SHAPES) > 256:
+            _HOST_SHAPES.clear()
+        hit = (spatial_shapes.cpu().numpy().astype("int64").copy(), level_start_index.cpu().numpy().astype("int64").copy())
+        _HOST_SHAPES[key] = hit
+    return hit
+
+
+def window_supported(value, S, Lq, L, P):
+    return (WINDOW_MODE != "off" and Lq == S and value.dtype in WINDOW_MARGIN and value.shape[-1] == 32 and 1 <= L <= 4
+            and L * P in (8, 16, 32) and value.numel() < 2 ** 31)
+
+
+def _pyramid_in_order(hs, hl, S):
+    """The window kernel reads a query's pixel from its index: levels must tile [0, S) back to back."""
+    start = 0
+    for (h, w), s0 in zip(hs.tolist(), hl.tolist()):
+        if h <= 0 or w <= 0 or s0 != start:
+            return False
+        start += h * w
+    return start == S
+
+
 def _loc_dtype(value):
     return torch.float64 if value.dtype == torch.float64 else torch.float32
 
@@ -71,6 +112,19 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     e = value.element_size()
     info = {"bytes": float(N) * (e * S * M * D + sampling_loc.element_size() * 3 * Lq * M * L * P + e * Lq * M * D),
             "N": N, "Lq": Lq, "S": S}
+    hs = hl = None
+    if window_supported(value, S, Lq, L, P):
+        hs, hl = host_geometry(spatial_shapes, level_start_index)
+    if hs is not None and _pyramid_in_order(hs, hl, S):
+        with torch.cuda.device(value.device):
+            rc = _cabi.timed_call(
+                "msda_win_enc", info, value,
+                lambda: _cabi.lib().vnext_msda_forward_selfattn(
+                    _DTYPES[value.dtype], value.data_ptr(), hs.ctypes.data, hl.ctypes.data, sampling_loc.data_ptr(),
+                    attn_weight.data_ptr(), None, 0, None, 0, 0, N, S, M, D, L, P, WINDOW_MARGIN[value.dtype],
+                    out.data_ptr(), _stream(value)))
+        _cabi.check(rc, "ms_deform_attn_forward (window)")
+        return out
     with torch.cuda.device(value.device):
         rc = _cabi.timed_call(
             "msda_fwd_enc" if Lq == S else "msda_fwd_dec", info, value,
@@ -82,9 +136,12 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     return out
 
 
-def ms_deform_attn_fused(value, spatial_shapes, level_start_index, offsets_logits, reference_points, n_levels, n_points):
+def ms_deform_attn_fused(value, spatial_shapes, level_start_index, offsets_logits, reference_points, n_levels, n_points,
+                         host_geom=None, margin=None):
     """Fused module core: softmax + sampling locations + sampling (include/vnext_b200.h: vnext_msda_forward_fused).
-    value [N,S,M,32]; offsets_logits [N,Lq,M*L*P*3] (rows may be strided); reference_points [N|1, Lq, L, 2|4]."""
+    value [N,S,M,32]; offsets_logits [N,Lq,M*L*P*3] (rows may be strided); reference_points [N|1, Lq, L, 2|4].
+    Lq == S (encoder self-attention) runs the shared-memory window kernel (vnext_msda_forward_selfattn); `host_geom` =
+    (shapes, level_start_index) as host int64 numpy arrays (else they are fetched once from the device and cached)."""
     if not value.is_cuda:
         raise RuntimeError("Not implemented on the CPU")
     N, S, M, D = value.shape
@@ -101,6 +158,20 @@ def ms_deform_attn_fused(value, spatial_shapes, level_start_index, offsets_logit
     out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
     e = value.element_size()
     info = {"bytes": float(N) * (e * S * M * D + 4 * 3 * Lq * M * L * P + e * Lq * M * D), "N": N, "Lq": Lq, "S": S}
+    hs = hl = None
+    if window_supported(value, S, Lq, L, P) and reference_points.shape[-1] == 2:
+        hs, hl = host_geom if host_geom is not None else host_geometry(spatial_shapes, level_start_index)
+    if hs is not None and _pyramid_in_order(hs, hl, S):
+        mg = WINDOW_MARGIN[value.dtype] if margin is None else margin
+        with torch.cuda.device(value.device):
+            rc = _cabi.timed_call(
+                "msda_win_fused_enc", info, value,
+                lambda: _cabi.lib().vnext_msda_forward_selfattn(
+                    _DTYPES[value.dtype], value.data_ptr(), hs.ctypes.data, hl.ctypes.data, None, None, ol.data_ptr(),
+                    ol.stride(0), reference_points.data_ptr(), reference_points.shape[-1],
+                    1 if reference_points.shape[0] == 1 else 0, N, S, M, D, L, P, mg, out.data_ptr(), _stream(value)))
+        _cabi.check(rc, "ms_deform_attn_fused (window)")
+        return out
     with torch.cuda.device(value.device):
         rc = _cabi.timed_call(
             "msda_fused_enc" if Lq == S else "msda_fused_dec", info, value,

@@ -14,13 +14,14 @@ class ClipRunner:
         self.engine, self.T, self.H, self.W = engine, T, H, W
         self.ori_size = tuple(ori_size) if ori_size is not None else (H, W)
         self.topk = topk
+        self.direct_h2d = False        # measured slower than one staged copy in round 1 (five small copies); kept selectable
         dev = engine.device
         self.frames_dev = torch.zeros(T, 3, H, W, dtype=torch.uint8, device=dev)
         self.frames_pin = torch.zeros(T, 3, H, W, dtype=torch.uint8).pin_memory()
         self.stream = torch.cuda.Stream(device=dev)
         # non-blocking stream: order it after whatever stream packed the engine's weights / built the ClipPlan
         self.stream.wait_stream(torch.cuda.current_stream(dev))
-        self.graph = None
+        self.graph = self.graph_head = None
         self._pending = None
         with torch.cuda.device(dev):
             with torch.cuda.stream(self.stream):
@@ -28,9 +29,16 @@ class ClipRunner:
                     self.scores, self.masks = self._device_step()
             self.stream.synchronize()
             if use_graph:
+                # two graphs sharing one memory pool: the small head (preprocess + backbone) is submitted in tens of
+                # microseconds, so the GPU is busy while the host submits the large tail — a single ~1000-node graph
+                # kept the GPU idle for the ~1.5 ms its launch takes (profiles/r02_stream_stress_and_e2e_breakdown.txt)
+                self.graph_head = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_head, stream=self.stream):
+                    self._feats = engine.infer_video_stage1(self.frames_dev)
                 self.graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph, stream=self.stream):
-                    self.scores, self.masks = self._device_step()
+                with torch.cuda.graph(self.graph, stream=self.stream, pool=self.graph_head.pool()):
+                    self.scores, self.masks = engine.infer_video_stage2(self._feats, self.frames_dev.shape, self.ori_size,
+                                                                        self.topk)
         self.h2d_bytes = self.frames_pin.numel()
         self.d2h_bytes = self.scores.numel() * 4 + self.masks.numel()
 
@@ -41,6 +49,7 @@ class ClipRunner:
         """Inputs already resident in HBM (self.frames_dev); enqueues one clip on self.stream."""
         with torch.cuda.stream(self.stream):          # graph.replay() launches on the *current* stream
             if self.graph is not None:
+                self.graph_head.replay()
                 self.graph.replay()
             else:
                 self.scores, self.masks = self._device_step()
@@ -57,7 +66,11 @@ class ClipRunner:
 
     def submit(self, frames_u8=None, frames_list=None):
         """Stage the frames and enqueue H2D + graph + D2H on this runner's stream without waiting (see collect())."""
-        if frames_list is not None:
+        direct = (frames_list is not None and self.direct_h2d and
+                  all(f.dtype == torch.uint8 and f.is_contiguous() and f.is_pinned() for f in frames_list))
+        if direct:
+            pass                                      # caller's frames are pinned uint8: no host staging copy
+        elif frames_list is not None:
             for i, f in enumerate(frames_list):
                 self.frames_pin[i].copy_(f)
         elif frames_u8 is not None:
@@ -66,7 +79,11 @@ class ClipRunner:
         masks_pin = torch.empty(self.masks.shape, dtype=self.masks.dtype, pin_memory=True)
         self.stream.wait_stream(torch.cuda.current_stream(self.frames_dev.device))
         with torch.cuda.stream(self.stream):
-            self.frames_dev.copy_(self.frames_pin, non_blocking=True)
+            if direct:
+                for i, f in enumerate(frames_list):
+                    self.frames_dev[i].copy_(f, non_blocking=True)
+            else:
+                self.frames_dev.copy_(self.frames_pin, non_blocking=True)
             self.run_device()
             scores_pin.copy_(self.scores, non_blocking=True)
             masks_pin.copy_(self.masks, non_blocking=True)
