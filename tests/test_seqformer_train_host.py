@@ -77,7 +77,10 @@ def test_train_forward_backward_matches_reference(monkeypatch, batched):
     worst, model = run("cpu", 1e-4, 2e-3, 2e-3, batched=batched)
     print("worst grad-norm rel err", worst)
     # encoder layers carry an `output_proj_box` the encode path never uses (ms_deform_attn.py:89-124): zero gradient
-    unused = [k for k, p in model.flat.params.items() if float(p.grad.abs().sum()) == 0]
+    # (the scalar bias of `time_attention_weights` is softmax-shift-invariant: its gradient is 0 up to rounding and
+    # may come out exactly 0 depending on the host's BLAS summation order)
+    unused = [k for k, p in model.flat.params.items() if float(p.grad.abs().sum()) == 0
+              and not k.endswith("time_attention_weights.bias")]
     assert unused and all("encoder" in k and "output_proj_box" in k for k in unused)
 
 
