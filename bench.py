@@ -432,7 +432,8 @@ def own_arm(args, rank, world, local_rank):
     for name, d in agg.items():
         f = ("gemm_tc_kernel" if name.startswith(("linear_", "conv3x3_")) else
              "msda_fwd_window_kernel" if name.startswith("msda_win") else
-             "msda_fwd_tile_kernel" if name.startswith("msda_") else name)
+             "msda_fwd_tile_kernel[encoder shape]" if name.startswith("msda_") and name.endswith("_enc") else
+             "msda_fwd_tile_kernel[decoder shape]" if name.startswith("msda_") else name)
         g = fam.setdefault(f, {"calls": 0, "us": 0.0, "bytes": 0.0, "flops": 0.0})
         for k in g:
             g[k] += d[k]
@@ -483,7 +484,8 @@ def own_arm(args, rank, world, local_rank):
                         "launches_per_step": d["calls"] // 3, "avg_us": round(d["us"] / d["calls"], 2),
                         "algorithmic_bytes_per_launch": round(d["bytes"] / d["calls"]),
                         "note": "sum of algorithmic bytes over the family's launches in a step / their summed CUDA-event time"}
-        for key, famname in (("msda_encoder", "msda_fwd_window_kernel"), ("msda_decoder", "msda_fwd_tile_kernel")):
+        for key, famname in (("msda_encoder", "msda_fwd_window_kernel"), ("msda_encoder", "msda_fwd_tile_kernel[encoder shape]"),
+                             ("msda_decoder", "msda_fwd_tile_kernel[decoder shape]")):
             if famname in fam:
                 m = fam[famname]
                 roofline[key] = {"kernel": famname, "achieved": round(m["bytes"] / m["us"] / 1e3, 1),
@@ -494,8 +496,8 @@ def own_arm(args, rank, world, local_rank):
         if tr:
             roofline["traffic"] = tr.get(top)
             roofline["traffic_source"] = tr.get("source")
-            if "msda_encoder" in roofline and tr.get("msda_fwd_window_kernel"):
-                roofline["msda_encoder"]["traffic"] = tr["msda_fwd_window_kernel"]
+            if "msda_encoder" in roofline and tr.get("msda_encoder"):
+                roofline["msda_encoder"]["traffic"] = tr["msda_encoder"]
 
     cpu = None
     if args.gpus == 1 and not args.no_cpu_baseline and swin is None:

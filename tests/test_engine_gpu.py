@@ -96,14 +96,15 @@ def test_tf32_mode_error_is_reported():
 
 
 def test_bf16_mode_error_is_reported():
-    """bf16 storage end to end (backbone, input projection, encoder, mask branch; BASELINE config 4's precision): within the
-    north star's 1e-2 of the fp32 oracle, relative to each output's scale."""
+    """bf16 mode (bf16 storage + bf16 MMAs in the backbone, the input projection and the encoder's value / sampled / FFN-hidden
+    tensors; fp32 residual stream; BASELINE config 4's precision): within the north star's 1e-2 of the fp32 oracle, relative
+    to each output's scale."""
     from vnext_b200.seqformer.engine import SeqFormerEngine
     T, H, W, seed = 3, 96, 128, 0
     sd = fill_state_dict(seqformer_r50_state_spec(), seed)
     frames = synthetic_clip(T, H, W, seed)
     out = SeqFormerEngine(sd, device="cuda", precision="bf16").inference(torch.stack(frames).cuda())
-    assert out["memory"].dtype == torch.bfloat16
+    assert out["memory"].dtype == torch.float32            # the encoder's residual stream stays fp32
     with torch.no_grad():
         ref = SO.inference(sd, frames, return_intermediates=True)
     errs = {k: _rel(out[k].float().cpu(), ref[k]) for k in ("pred_logits", "pred_boxes", "pred_masks")}

@@ -16,9 +16,13 @@ PYR720 = [(92, 160), (46, 80), (23, 40), (12, 20)]
 
 @pytest.fixture(scope="module")
 def ops():
+    """The op layer with the (opt-in) window kernel switched on for this module."""
     from vnext_b200 import _cabi, msda
     _cabi.lib()
-    return msda
+    prev = msda.WINDOW_MODE
+    msda.WINDOW_MODE = "auto"
+    yield msda
+    msda.WINDOW_MODE = prev
 
 
 def _variant():

@@ -12,7 +12,8 @@ from vnext_b200.seqformer.engine import SeqFormerEngine  # noqa: E402
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "720p"
 T, H, W = bench.WORKLOADS[wl]
-eng = SeqFormerEngine(bench.make_weights(0), device="cuda", precision="tf32")
+precision = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+eng = SeqFormerEngine(bench.make_weights(0), device="cuda", precision=precision)
 frames = bench.make_clip_u8(T, H, W, 0).cuda()
 for _ in range(2):
     eng.infer_video_device(frames, (H, W))
@@ -20,5 +21,8 @@ with _cabi.KernelTimer() as kt:
     for _ in range(3):
         eng.infer_video_device(frames, (H, W))
 agg = kt.summary()
+tot = sum(d["us"] for d in agg.values()) / 3
+print(f"# {wl} {precision}: {tot:.0f} us of C-ABI kernel time per clip (eager, per-launch CUDA events)")
 for name, d in sorted(agg.items(), key=lambda kv: -kv[1]["us"])[:int(os.environ.get("TOPN", "8"))]:
-    print(f"{name:34s} calls/step {d['calls'] // 3:3d}  avg {d['us'] / d['calls']:8.1f} us  {d['bytes'] / d['us'] / 1e3:8.1f} GB/s")
+    print(f"{name:40s} calls/step {d['calls'] // 3:3d}  avg {d['us'] / d['calls']:8.1f} us  total {d['us'] / 3:8.1f} us  "
+          f"{d['bytes'] / d['us'] / 1e3:8.1f} GB/s  {d['flops'] / d['us'] / 1e6:7.1f} TF/s")

@@ -60,7 +60,7 @@ def main():
                     rec[f"{name}_{tag}_us"] = round(med, 1)
                     rec[f"{name}_{tag}_GBps"] = round(alg / med / 1e3, 1)
                     rec[f"{name}_{tag}_frac"] = round(alg / med / 1e3 / hbm, 4)
-                msda.WINDOW_MODE = "auto"
+                msda.WINDOW_MODE = "off"
                 rec[f"alg_MB_{tag}"] = round(alg / 1e6, 1)
             if stock is not None:
                 med, _ = time_fn(lambda: stock.ms_deform_attn_forward(dv, dsh, dlsi, dloc, dattn, 64), args.iters, flush)

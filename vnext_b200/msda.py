@@ -57,28 +57,30 @@ def _check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_w
 
 # ---------------------------------------------------------------- self-attention (encoder shape) window kernel
 # "auto": use the shared-memory window kernel whenever the queries are the pixel grid (Lq == S) and the shape is
-# supported; "off": never.  The window kernel is exact for any sampling locations (out-of-window samples are read
-# from global memory), it is just slower than the tile kernel when the locations have no spatial locality.
-WINDOW_MODE = "auto"
+# supported; "off": never (default).  The window kernel is exact for any sampling locations (out-of-window samples are
+# read from global memory).  Measured on the B200 (profiles/r02_msda_window_*.txt) it removes the L2 -> L1 gather that
+# bounds the tile kernel (L2 sectors 5.0 GB -> 1.2 GB per 720p launch) but ends up bound by shared-memory wavefronts and
+# issue slots at 16 warps/SM: 433 us (bf16 value) / 600 us (fp32) against 311 / 387 us for the tile kernel at 32 warps/SM,
+# so the tile kernel stays the default and this path is opt-in.
+WINDOW_MODE = "off"
 WINDOW_MARGIN = {torch.float32: 4, torch.bfloat16: 6}      # pixels around the tile footprint staged per level
-_HOST_SHAPES = {}
 
 
 def host_geometry(spatial_shapes, level_start_index):
-    """HOST copies (numpy int64) of the two geometry tensors, cached per tensor (one device sync per new tensor; the
-    engines pass their plan's host copies instead and never hit this)."""
-    key = (spatial_shapes.data_ptr(), spatial_shapes._version, level_start_index.data_ptr(), level_start_index._version,
-           spatial_shapes.device.index)
-    hit = _HOST_SHAPES.get(key)
-    if hit is None:
+    """HOST copies (numpy int64) of the two geometry tensors.  The copy is kept ON the shapes tensor object itself
+    (an attribute, validated against both tensors' in-place version counters and the identity of the index tensor), so a
+    recycled device address can never serve another tensor's geometry; one device sync per new tensor (the engines pass
+    their plan's host copies instead and never hit this)."""
+    tag = (spatial_shapes._version, id(level_start_index), level_start_index._version)
+    hit = getattr(spatial_shapes, "_vnext_host_geom", None)
+    if hit is None or hit[0] != tag:
         if torch.cuda.is_current_stream_capturing():
             raise RuntimeError("ms_deform_attn: spatial_shapes must be known on the host before CUDA-graph capture "
                                "(call msda.host_geometry(shapes, lsi) once outside the capture)")
-        if len(_HOST_SHAPES) > 256:
-            _HOST_SHAPES.clear()
-        hit = (spatial_shapes.cpu().numpy().astype("int64").copy(), level_start_index.cpu().numpy().astype("int64").copy())
-        _HOST_SHAPES[key] = hit
-    return hit
+        hit = (tag, spatial_shapes.cpu().numpy().astype("int64").copy(), level_start_index.cpu().numpy().astype("int64").copy(),
+               level_start_index)          # keeps the index tensor alive so its id() stays unique
+        spatial_shapes._vnext_host_geom = hit
+    return hit[1], hit[2]
 
 
 def window_supported(value, S, Lq, L, P):
