@@ -83,6 +83,26 @@ def test_residual_relu_bias2d_and_row_mask():
     assert (out[mask.bool().repeat(M // S), :256] == 0).all()
 
 
+@pytest.mark.parametrize("S,M", [(200, 1000), (136, 1000), (8, 300), (19560, 3 * 19560)])
+def test_periodic_bias2d_staged_by_tma(S, M):
+    """period % 8 == 0: the row-periodic 2-D bias tile goes through shared memory as four 8-row TMA boxes (a 32-row tile may
+    wrap around the period at any multiple of 8); fp32 and bf16 operands, fp32 and bf16 outputs."""
+    from vnext_b200.linear import linear
+    N, K = 384, 256
+    x, w, _ = _mk(M, N, K, 7)
+    b2 = torch.randn(S, N, generator=torch.Generator().manual_seed(8)).cuda()
+    rep = b2.double().repeat(M // S + 1, 1)[:M]
+    want = F.linear(x.double(), w.double()) + rep
+    tol = 2e-3 * want.abs().max().item()
+    out = linear(x, w, None, bias2d=b2)
+    assert (out.double() - want).abs().max().item() < tol
+    out16 = linear(x, w, None, bias2d=b2, out_dtype=torch.bfloat16)
+    assert (out16.double() - want).abs().max().item() < 4 * tol
+    outb = linear(x.bfloat16(), w.bfloat16(), None, bias2d=b2, out_dtype=torch.float32)
+    wantb = F.linear(x.bfloat16().double(), w.bfloat16().double()) + rep
+    assert (outb.double() - wantb).abs().max().item() < 2e-5 * want.abs().max().item()
+
+
 @pytest.mark.parametrize("T,H,W,Cin,Cout", [(2, 23, 40, 64, 64), (1, 8, 16, 32, 128), (3, 46, 80, 256, 256),
                                            (1, 184, 320, 64, 64), (2, 13, 17, 128, 8), (5, 92, 160, 256, 64)])
 def test_conv3x3_implicit_gemm(T, H, W, Cin, Cout):

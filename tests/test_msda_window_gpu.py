@@ -1,4 +1,5 @@
-"""GPU parity of the self-attention (encoder-shape) window kernel `vnext_msda_forward_selfattn` (csrc/msda_window.cu):
+"""GPU parity of the self-attention (encoder-shape) kernels behind `vnext_msda_forward_selfattn` — the cache-blocked one
+(csrc/msda_cached.cu, the default) and the shared-memory window one (csrc/msda_window.cu, opt-in); every test runs for both:
 against the C oracle (restating ms_deform_im2col_cuda.cuh:237-299), against the tile kernel on the same inputs, for
 local (windowed), far (global-path) and out-of-range sampling locations, fp32 and bf16 value, both front-ends."""
 import numpy as np
@@ -14,13 +15,17 @@ PYR = [(60, 108), (30, 54), (15, 27), (8, 14)]
 PYR720 = [(92, 160), (46, 80), (23, 40), (12, 20)]
 
 
-@pytest.fixture(scope="module")
-def ops():
-    """The op layer with the (opt-in) window kernel switched on for this module."""
+KIND = {"auto": "window", "cached": "cached"}
+
+
+@pytest.fixture(scope="module", params=["cached", "auto"])
+def ops(request):
+    """The op layer with one of the two self-attention kernels selected for this module run."""
     from vnext_b200 import _cabi, msda
     _cabi.lib()
     prev = msda.WINDOW_MODE
-    msda.WINDOW_MODE = "auto"
+    msda.WINDOW_MODE = request.param
+    msda.TEST_MODE = request.param
     yield msda
     msda.WINDOW_MODE = prev
 
@@ -65,15 +70,15 @@ def test_window_fp32_matches_oracle_and_tile_kernel(ops, pyr, N, M, K, sigma, ou
     value, shapes, lsi, loc, attn = encoder_inputs(N, M, pyr, K, 11, sigma, outlier)
     dv = _cuda(value, shapes, lsi, loc, attn)
     out = ops.ms_deform_attn_forward(*dv, 64).cpu()
-    assert _variant() == "fwd_window_f32"
+    assert _variant() == f"fwd_{KIND[ops.TEST_MODE]}_f32"
     oc = O.forward_c(value, shapes, lsi, loc, attn, np.float32)
     assert torch.allclose(out, oc, rtol=1e-4, atol=1e-7)
     ops.WINDOW_MODE = "off"
     try:
         tile = ops.ms_deform_attn_forward(*dv, 64).cpu()
-        assert not _variant().startswith("fwd_window")
+        assert not _variant().startswith(("fwd_window", "fwd_cached"))
     finally:
-        ops.WINDOW_MODE = "auto"
+        ops.WINDOW_MODE = ops.TEST_MODE
     assert torch.allclose(out, tile, rtol=1e-5, atol=1e-8)
 
 
@@ -81,7 +86,7 @@ def test_window_random_locations_everything_on_the_global_path(ops):
     """No locality at all (uniform locations incl. out of range): the window is only a cache, results stay exact."""
     value, shapes, lsi, loc, attn = O.make_inputs(2, sum(h * w for h, w in SMALL), 8, 32, SMALL, 4, 5, loc_range=(-0.2, 1.2))
     out = ops.ms_deform_attn_forward(*_cuda(value, shapes, lsi, loc, attn), 64).cpu()
-    assert _variant() == "fwd_window_f32"
+    assert _variant() == f"fwd_{KIND[ops.TEST_MODE]}_f32"
     assert torch.allclose(out, O.forward_c(value, shapes, lsi, loc, attn, np.float32), rtol=1e-4, atol=1e-7)
 
 
@@ -99,7 +104,7 @@ def test_window_nonfinite_locations_are_skipped_like_the_reference(ops):
 def test_window_bf16_value(ops, pyr, K):
     value, shapes, lsi, loc, attn = encoder_inputs(2 if pyr is SMALL else 1, 8, pyr, K, 7, dtype=torch.bfloat16)
     out = ops.ms_deform_attn_forward(*_cuda(value, shapes, lsi, loc, attn), 64)
-    assert _variant() == "fwd_window_bf16" and out.dtype == torch.bfloat16
+    assert _variant() == f"fwd_{KIND[ops.TEST_MODE]}_bf16" and out.dtype == torch.bfloat16
     ref = O.forward_c(value.float(), shapes, lsi, loc, attn, np.float32)       # exact on the bf16-rounded value
     assert torch.allclose(out.float().cpu(), ref, rtol=8e-3, atol=1e-6)           # one bf16 rounding of the output
 
@@ -120,7 +125,7 @@ def test_window_fused_front_end_matches_the_fused_tile_kernel(ops, dtype, ref_di
     dv, ds, dl, doa, dref = _cuda(value, shapes, lsi, oa, ref)
     out = ops.ms_deform_attn_fused(dv, ds, dl, doa, dref, L, K)
     if ref_dim == 2:
-        assert _variant() == ("fwd_window_fused_f32" if dtype == torch.float32 else "fwd_window_fused_bf16")
+        assert _variant() == f"fwd_{KIND[ops.TEST_MODE]}_fused_" + ("f32" if dtype == torch.float32 else "bf16")
     else:
         assert _variant().startswith("fwd_fused_")         # box-shaped references (decoder) stay on the tile kernel
     ops.WINDOW_MODE = "off"
@@ -128,7 +133,7 @@ def test_window_fused_front_end_matches_the_fused_tile_kernel(ops, dtype, ref_di
         tile = ops.ms_deform_attn_fused(dv, ds, dl, doa, dref, L, K)
         assert _variant().startswith("fwd_fused_")
     finally:
-        ops.WINDOW_MODE = "auto"
+        ops.WINDOW_MODE = ops.TEST_MODE
     tol = dict(rtol=1e-5, atol=1e-8) if dtype == torch.float32 else dict(rtol=8e-3, atol=1e-6)
     assert torch.allclose(out.float(), tile.float(), **tol)
 
@@ -139,12 +144,12 @@ def test_window_full_size_720p_equals_tile_kernel(ops):
     value, shapes, lsi, loc, attn = encoder_inputs(5, 8, PYR720, 4, 1, 1.6, 0.01)
     dv = _cuda(value, shapes, lsi, loc, attn)
     out = ops.ms_deform_attn_forward(*dv, 64)
-    assert _variant() == "fwd_window_f32"
+    assert _variant() == f"fwd_{KIND[ops.TEST_MODE]}_f32"
     ops.WINDOW_MODE = "off"
     try:
         tile = ops.ms_deform_attn_forward(*dv, 64)
     finally:
-        ops.WINDOW_MODE = "auto"
+        ops.WINDOW_MODE = ops.TEST_MODE
     assert torch.allclose(out, tile, rtol=1e-5, atol=1e-8)
     sub = slice(0, 1)                                                 # one frame against the C oracle
     oc = O.forward_c(value[sub], shapes, lsi, loc[sub], attn[sub], np.float32)
@@ -158,6 +163,6 @@ def test_unordered_levels_fall_back_to_the_tile_kernel(ops):
     lsi2 = torch.tensor([60, 0])                                      # level 1 stored first
     value2 = torch.cat((value[:, 240:], value[:, :240]), 1).contiguous()
     out = ops.ms_deform_attn_forward(*_cuda(value2, shapes, lsi2, loc, attn), 64).cpu()
-    assert not _variant().startswith("fwd_window")
+    assert not _variant().startswith(("fwd_window", "fwd_cached"))
     ref = ops.ms_deform_attn_forward(*_cuda(value, shapes, lsi, loc, attn), 64).cpu()
     assert torch.allclose(out, ref, rtol=1e-5, atol=1e-8) and S == 300

@@ -52,11 +52,12 @@ def main():
             for dtype, tag, e in ((torch.float32, "f32", 4), (torch.bfloat16, "bf16", 2)):
                 v = dv.to(dtype)
                 alg = N * (e * S * M * D + 4 * 3 * S * M * 4 * K + e * S * M * D)
-                for mode in ("auto", "off"):
+                for mode in ("cached", "auto", "off"):
                     msda.WINDOW_MODE = mode
                     med, best = time_fn(lambda: msda.ms_deform_attn_forward(v, dsh, dlsi, dloc, dattn, 64), args.iters, flush)
-                    name = "window" if mode == "auto" else "tile"
+                    name = {"auto": "window", "off": "tile", "cached": "cached"}[mode]
                     assert _cabi.last_variant().startswith("fwd_window") == (mode == "auto"), _cabi.last_variant()
+                    assert _cabi.last_variant().startswith("fwd_cached") == (mode == "cached"), _cabi.last_variant()
                     rec[f"{name}_{tag}_us"] = round(med, 1)
                     rec[f"{name}_{tag}_GBps"] = round(alg / med / 1e3, 1)
                     rec[f"{name}_{tag}_frac"] = round(alg / med / 1e3 / hbm, 4)
@@ -65,6 +66,8 @@ def main():
             if stock is not None:
                 med, _ = time_fn(lambda: stock.ms_deform_attn_forward(dv, dsh, dlsi, dloc, dattn, 64), args.iters, flush)
                 rec["stock_f32_us"] = round(med, 1)
+                rec["cached_f32_vs_stock"] = round(med / rec["cached_f32_us"], 2)
+                rec["cached_bf16_vs_stock_f32"] = round(med / rec["cached_bf16_us"], 2)
                 rec["window_f32_vs_stock"] = round(med / rec["window_f32_us"], 2)
                 rec["window_bf16_vs_stock_f32"] = round(med / rec["window_bf16_us"], 2)
                 rec["tile_f32_vs_stock"] = round(med / rec["tile_f32_us"], 2)

@@ -40,6 +40,9 @@ int msda_backward_device(int dtype, const void *value, const int64_t *shapes, co
                          void *gvalue, void *gloc, void *gattn, void *workspace, cudaStream_t stream);
 
 bool msda_window_supported(int dtype, int D, int L, int K);
+int msda_forward_cached_device(int dtype, const void *value, const int64_t *hshapes, const int64_t *hlsi, const float *loc,
+                               const float *attn, const float *oa, int oa_pitch, const float *ref, int ref_dim,
+                               int ref_shared, int N, int S, int M, int L, int K, void *out, cudaStream_t stream);
 int msda_forward_window_device(int dtype, const void *value, const int64_t *hshapes, const int64_t *hlsi, const float *loc,
                                const float *attn, const float *oa, int oa_pitch, const float *ref, int ref_dim,
                                int ref_shared, int N, int S, int M, int L, int K, int margin, void *out,
@@ -126,6 +129,12 @@ int vnext_msda_forward_selfattn(int dtype, const void *value, const int64_t *spa
     VNEXT_CHECK_ARG(channels == 32 && msda_window_supported(dtype, channels, num_levels, num_point),
                     "vnext_msda_forward_selfattn: needs channels == 32, num_levels <= 4, num_levels*num_point in {8,16,32}, "
                     "fp32/bf16 value (got D=%d L=%d K=%d dtype=%d)", channels, num_levels, num_point, dtype);
+    if (margin < 0)      // cache-blocked variant (csrc/msda_cached.cu): no shared-memory windows, the L1 does the staging
+        return msda_forward_cached_device(dtype, value, spatial_shapes_host, level_start_index_host,
+                                          static_cast<const float *>(sampling_loc), static_cast<const float *>(attn_weight),
+                                          offsets_logits, row_pitch, reference_points, ref_dim, ref_shared, batch,
+                                          spatial_size, num_heads, num_levels, num_point, output,
+                                          static_cast<cudaStream_t>(stream));
     return msda_forward_window_device(dtype, value, spatial_shapes_host, level_start_index_host,
                                       static_cast<const float *>(sampling_loc), static_cast<const float *>(attn_weight),
                                       offsets_logits, row_pitch, reference_points, ref_dim, ref_shared, batch, spatial_size,

@@ -167,6 +167,7 @@ struct GemmParams {
     const float *bias;       // [N] or null
     const float *bias2d;     // [period, ldb2] or null: added as bias2d[row % period][col] (geometry-dependent bias)
     int period, ldb2;
+    int b2_tma;              // the 2-D bias tile comes through shared memory (four 8-row TMA boxes, rows taken mod period)
     const unsigned char *row_mask;   // [period] or null: rows with mask != 0 get columns [0, mask_cols) zeroed
     int mask_cols;
     const float *residual;   // [M, ldr] (EPI_RESIDUAL)
@@ -197,7 +198,7 @@ constexpr int BLOCK_M = 128;
 // the TMA path is unavailable (unaligned rows)
 __device__ __forceinline__ void epilogue_add_global(const GemmParams &p, int row, bool row_ok, int col0, uint32_t (&v)[32]) {
     if (!row_ok) return;
-    const float *b2 = p.bias2d ? p.bias2d + (size_t)(row % p.period) * p.ldb2 + col0 : nullptr;
+    const float *b2 = (p.bias2d && !p.b2_tma) ? p.bias2d + (size_t)(row % p.period) * p.ldb2 + col0 : nullptr;
     const float *rr = ((p.flags & EPI_RESIDUAL) && !p.tma_epi) ? p.residual + (size_t)row * p.ldr + col0 : nullptr;
     const bool vec = p.vec_ok && (col0 + 32 <= p.N);
 #pragma unroll
@@ -343,18 +344,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const bool relu = (p.flags & EPI_RELU) != 0;
         const bool has_res = (p.flags & EPI_RESIDUAL) != 0;
         const bool tma_epi = p.tma_epi != 0;
+        const bool b2_tma = p.b2_tma != 0;                          // (never together with a residual)
+        const bool addend = has_res || b2_tma;                      // a 32 x 32 tile added to the accumulator, staged by TMA
+
         const bool ln = (p.flags & EPI_LAYERNORM) != 0;
         // staging: two 4-KB tiles (32 rows x 128 B, SWIZZLE_128B) per warp.  With a residual: [0] = out, [1] = residual;
         // without: both are output buffers (double-buffered TMA stores).
         unsigned char *const buf0 = epi_smem + ewi * 8192;
         unsigned char *const buf1 = buf0 + 4096;
+        // one addend tile -> buf1: the residual's rows row0..row0+31, or the periodic bias rows (row0 + r) % period, which
+        // are four 8-row boxes because the period need not be a multiple of 32 (it is a multiple of 8, checked on the host)
+        auto load_addend = [&](int col, int row0_) {
+            mbar_expect_tx(&res_bar[ewi], b2_tma ? 4096u : EPI_TILE_BYTES);
+            if (b2_tma) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    tma_load_2d(buf1 + q * 1024, &tmap_res, col, (row0_ + 8 * q) % p.period, &res_bar[ewi]);
+            } else {
+                tma_load_2d(buf1, &tmap_res, col, row0_, &res_bar[ewi]);
+            }
+        };
         const int swz = lane & 7;                                   // 16-B chunk j of row r lives at j ^ (r & 7)
         const int swz64 = (lane >> 1) & 3;                          // same for the 64-B rows of a bf16 tile
         uint32_t stores = 0, res_loads = 0;
         int bias_n_idx = -1;
         if (tma_epi && lane == 0) {
             prefetch_tmap(&tmap_out);
-            if (has_res) prefetch_tmap(&tmap_res);
+            if (addend) prefetch_tmap(&tmap_res);
         }
         for (int work = first_work; work < num_work; work += work_stride) {
             const int tile = work_tile(work);
@@ -377,11 +393,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 bias_n_idx = n_idx;
             }
-            if (tma_epi && has_res && half < n_chunks) {                // first residual tile: in flight while we wait
-                if (lane == 0) {
-                    mbar_expect_tx(&res_bar[ewi], EPI_TILE_BYTES);
-                    tma_load_2d(buf1, &tmap_res, n_idx + half * 32, row0, &res_bar[ewi]);
-                }
+            if (tma_epi && addend && half < n_chunks) {                 // first addend tile: in flight while we wait
+                if (lane == 0) load_addend(n_idx + half * 32, row0);
             }
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
@@ -401,10 +414,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     tmem_ld_wait();
                     if ((pass == 0 || !ln) && !(p.flags & 0x200)) {
                         const unsigned char *rrow = nullptr;
-                        if (tma_epi && has_res) {
+                        if (tma_epi && addend) {
                             mbar_wait(&res_bar[ewi], res_loads & 1);
                             ++res_loads;
-                            rrow = buf1 + lane * (OUT16 ? 64 : 128);
+                            rrow = buf1 + lane * ((OUT16 && !b2_tma) ? 64 : 128);
                         }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {                    // bias from shared memory (broadcast reads)
@@ -413,7 +426,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                                    __uint_as_float(v[4 * j + 2]) + b.z, __uint_as_float(v[4 * j + 3]) + b.w);
                             if (rrow) {
                                 float4 r;
-                                if (OUT16)     // 64-B rows, SWIZZLE_64B: 16-B chunk c of row r lives at c ^ ((r >> 1) & 3)
+                                if (OUT16 && !b2_tma)     // 64-B rows, SWIZZLE_64B: 16-B chunk c of row r lives at c ^ ((r >> 1) & 3)
                                     r = load4(reinterpret_cast<const __nv_bfloat16 *>(rrow + (((j >> 1) ^ swz64) << 4) + (j & 1) * 8));
                                 else
                                     r = *reinterpret_cast<const float4 *>(rrow + ((j ^ swz) << 4));
@@ -424,12 +437,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         }
                         if (rrow) {
                             __syncwarp();                                // tile consumed by all lanes -> refill it
-                            if (lane == 0 && c + 2 < n_chunks) {
-                                mbar_expect_tx(&res_bar[ewi], EPI_TILE_BYTES);
-                                tma_load_2d(buf1, &tmap_res, col0 + 64, row0, &res_bar[ewi]);
-                            }
+                            if (lane == 0 && c + 2 < n_chunks) load_addend(col0 + 64, row0);
                         }
-                        if (p.bias2d || (has_res && !rrow)) epilogue_add_global(p, row, row_ok, col0, v);
+                        if ((p.bias2d && !b2_tma) || (has_res && !rrow)) epilogue_add_global(p, row, row_ok, col0, v);
                     }
                     if (pass == 0) {
 #pragma unroll
@@ -470,8 +480,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     }
                     if (p.flags & 0x100) continue;                       // debug: no output at all
                     if (tma_epi) {
-                        unsigned char *ob = (has_res || !(stores & 1)) ? buf0 : buf1;
-                        const int pending_ok = has_res ? 0 : 1;          // groups that may still be reading shared memory
+                        unsigned char *ob = (addend || !(stores & 1)) ? buf0 : buf1;
+                        const int pending_ok = addend ? 0 : 1;           // groups that may still be reading shared memory
                         if (stores > (uint32_t)pending_ok) {
                             if (lane == 0) {
                                 if (pending_ok) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
@@ -695,6 +705,7 @@ int linear_tc_device(const LinearArgs &x, cudaStream_t stream) {
     p.num_m_tiles = p.num_n_tiles = 0;
     p.conv = p.conv_cin_blocks = p.conv_tiles_x = p.conv_tiles_y = 0;
     p.cluster = 1;
+    p.b2_tma = 0;
     p.vec_ok = al16(x.out) && x.ldo % oe == 0 && (!x.bias || al16(x.bias)) &&
                (!x.bias2d || (al16(x.bias2d) && x.ldb2 % 4 == 0)) && (!x.residual || (al16(x.residual) && x.ldr % oe == 0));
     // 256-wide tiles only when N is a multiple of 256.  Measured (720p encoder offsets|logits projection, N = 384):
@@ -733,6 +744,11 @@ int linear_tc_device(const LinearArgs &x, cudaStream_t stream) {
         if (x.residual) {
             rc = make_tmap_2d(&tr, x.out_dt, x.residual, x.M, x.N, x.ldr, 32, 32);
             if (rc) return rc;
+        } else if (x.bias2d && p.period % 8 == 0 && al16(x.bias2d) && x.ldb2 % 4 == 0 && x.N % 4 == 0) {
+            // row-periodic 2-D bias as a TMA-staged addend (8-row boxes: a 32-row tile may wrap around the period)
+            rc = make_tmap_2d(&tr, VNEXT_F32, x.bias2d, p.period, x.N, x.ldb2, 8, 32);
+            if (rc) return rc;
+            p.b2_tma = 1;
         }
     }
     return launch_any(wide, x.in_dt, x.out_dt, ta, tb, to, tr, p, stream);
@@ -743,6 +759,7 @@ int conv3x3_tc_device(int in_dt, int out_dt, const void *x, const void *w, const
     const int kbox = in_dt == VNEXT_BF16 ? 64 : 32;
     GemmParams p;
     p.M = T * H * W; p.N = Cout; p.K = 9 * Cin; p.bias = bias; p.bias2d = nullptr; p.period = 1; p.ldb2 = 0;
+    p.b2_tma = 0;
     p.row_mask = nullptr; p.mask_cols = 0; p.residual = nullptr; p.gamma = p.beta = nullptr; p.out = static_cast<float *>(out);
     p.ldo = Cout; p.ldr = 0; p.flags = relu ? EPI_RELU : 0; p.eps = 0.f; p.vec_ok = 1; p.tma_epi = 1;
     p.conv = 1; p.conv_cin_blocks = Cin / kbox; p.conv_tiles_x = (W + 15) / 16; p.conv_tiles_y = (H + 7) / 8;

@@ -55,13 +55,15 @@ def _check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_w
     return N, S, M, D, L, Lq, P
 
 
-# ---------------------------------------------------------------- self-attention (encoder shape) window kernel
-# "auto": use the shared-memory window kernel whenever the queries are the pixel grid (Lq == S) and the shape is
-# supported; "off": never (default).  The window kernel is exact for any sampling locations (out-of-window samples are
-# read from global memory).  Measured on the B200 (profiles/r02_msda_window_*.txt) it removes the L2 -> L1 gather that
-# bounds the tile kernel (L2 sectors 5.0 GB -> 1.2 GB per 720p launch) but ends up bound by shared-memory wavefronts and
-# issue slots at 16 warps/SM: 433 us (bf16 value) / 600 us (fp32) against 311 / 387 us for the tile kernel at 32 warps/SM,
-# so the tile kernel stays the default and this path is opt-in.
+# ---------------------------------------------------------------- self-attention (encoder shape) kernels
+# When the queries are the pixel grid (Lq == S: encoder self-attention) two more kernels exist besides the tile kernel,
+# both exact for ANY sampling locations (include/vnext_b200.h: vnext_msda_forward_selfattn):
+#   "cached": cache-blocked (csrc/msda_cached.cu) — 2-D query tiles x one head per work unit, 32 warps/SM, the L1 keeps
+#             what neighbouring queries share (the tile kernel re-fetches it from L2: 5 GB of L2 sectors per 720p launch);
+#   "auto":   shared-memory windows staged by TMA (csrc/msda_window.cu).  Removes the L2 traffic too, but at 16 warps/SM it
+#             is bound by shared-memory wavefronts / issue slots: 433 us (bf16 value) / 600 us (fp32) at 720p against
+#             311 / 387 us for the tile kernel (profiles/r02_msda_window_*): kept as an opt-in;
+#   "off":    always the tile kernel.
 WINDOW_MODE = "off"
 WINDOW_MARGIN = {torch.float32: 4, torch.bfloat16: 6}      # pixels around the tile footprint staged per level
 
@@ -81,6 +83,10 @@ def host_geometry(spatial_shapes, level_start_index):
                level_start_index)          # keeps the index tensor alive so its id() stays unique
         spatial_shapes._vnext_host_geom = hit
     return hit[1], hit[2]
+
+
+def _selfattn_margin(value):
+    return -1 if WINDOW_MODE == "cached" else WINDOW_MARGIN[value.dtype]
 
 
 def window_supported(value, S, Lq, L, P):
@@ -120,10 +126,10 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     if hs is not None and _pyramid_in_order(hs, hl, S):
         with torch.cuda.device(value.device):
             rc = _cabi.timed_call(
-                "msda_win_enc", info, value,
+                "msda_cached_enc" if WINDOW_MODE == "cached" else "msda_win_enc", info, value,
                 lambda: _cabi.lib().vnext_msda_forward_selfattn(
                     _DTYPES[value.dtype], value.data_ptr(), hs.ctypes.data, hl.ctypes.data, sampling_loc.data_ptr(),
-                    attn_weight.data_ptr(), None, 0, None, 0, 0, N, S, M, D, L, P, WINDOW_MARGIN[value.dtype],
+                    attn_weight.data_ptr(), None, 0, None, 0, 0, N, S, M, D, L, P, _selfattn_margin(value),
                     out.data_ptr(), _stream(value)))
         _cabi.check(rc, "ms_deform_attn_forward (window)")
         return out
@@ -164,10 +170,10 @@ def ms_deform_attn_fused(value, spatial_shapes, level_start_index, offsets_logit
     if window_supported(value, S, Lq, L, P) and reference_points.shape[-1] == 2:
         hs, hl = host_geom if host_geom is not None else host_geometry(spatial_shapes, level_start_index)
     if hs is not None and _pyramid_in_order(hs, hl, S):
-        mg = WINDOW_MARGIN[value.dtype] if margin is None else margin
+        mg = _selfattn_margin(value) if margin is None else margin
         with torch.cuda.device(value.device):
             rc = _cabi.timed_call(
-                "msda_win_fused_enc", info, value,
+                "msda_cached_fused_enc" if WINDOW_MODE == "cached" else "msda_win_fused_enc", info, value,
                 lambda: _cabi.lib().vnext_msda_forward_selfattn(
                     _DTYPES[value.dtype], value.data_ptr(), hs.ctypes.data, hl.ctypes.data, None, None, ol.data_ptr(),
                     ol.stride(0), reference_points.data_ptr(), reference_points.shape[-1],

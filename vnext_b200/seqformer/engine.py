@@ -103,6 +103,10 @@ class SeqFormerEngine:
         if precision == "bf16" and not self.native:
             raise RuntimeError("precision='bf16' exists only on the CUDA kernels")
         self.act_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        import os
+        parts = os.environ.get("VNEXT_BF16_PARTS", "backbone,encoder").split(",")     # experiment switch (tools/bf16_error_budget.py)
+        self.bb_dtype = self.act_dtype if "backbone" in parts else torch.float32      # backbone + input projection storage
+        self.enc_dtype = self.act_dtype if "encoder" in parts else torch.float32      # encoder value / sampled / FFN hidden
         self._plans: Dict[Tuple[int, int, int], ClipPlan] = {}
         self._khwc = {}
         self._wcast = {}
@@ -319,7 +323,7 @@ class SeqFormerEngine:
         """frames [T,3,H,W] uint8/float (0..255) on device -> normalised, zero-padded channels-last [T,3,Hp,Wp]."""
         if self.native:
             from .. import fused
-            x = fused.preprocess(frames.contiguous(), self._mean3, self._std3, plan.Hp, plan.Wp, out_dtype=self.act_dtype)
+            x = fused.preprocess(frames.contiguous(), self._mean3, self._std3, plan.Hp, plan.Wp, out_dtype=self.bb_dtype)
             return x.permute(0, 3, 1, 2)                  # logical NCHW over NHWC memory (= channels_last)
         x = (frames.float() - self.pixel_mean) / self.pixel_std
         if plan.any_pad:
@@ -419,7 +423,7 @@ class SeqFormerEngine:
     def _value(self, x, attn_w, plan):
         if self.native_gemm:      # padding rows zeroed in the GEMM epilogue
             kw = {"row_mask": plan.extra["mask_u8"], "mask_cols": self.C} if plan.any_pad else {}
-            v = self.lin(x, (attn_w["v_w"], attn_w["v_b"]), out_dtype=self.act_dtype, **kw)
+            v = self.lin(x, (attn_w["v_w"], attn_w["v_b"]), out_dtype=self.enc_dtype, **kw)
         else:
             v = F.linear(x, attn_w["v_w"], attn_w["v_b"])
             if plan.any_pad:
@@ -436,7 +440,7 @@ class SeqFormerEngine:
             s = self.sample(self._value(x, a, plan), oa, plan.enc_ref, plan, a["n_off"])
             if self.native_gemm:     # branch tensors in act_dtype (bf16 in bf16 mode), residual stream x in fp32
                 x = self.lin(s, (a["o_w"], a["o_b"]), residual=x, ln=w["norm1"], out_dtype=torch.float32)
-                h = self.lin(x, w["lin1"], relu=True, out_dtype=self.act_dtype)
+                h = self.lin(x, w["lin1"], relu=True, out_dtype=self.enc_dtype)
                 x = self.lin(h, w["lin2"], residual=x, ln=w["norm2"], out_dtype=torch.float32)
             else:
                 x = self.lin(s, (a["o_w"], a["o_b"]), residual=x, ln=w["norm1"])
