@@ -189,6 +189,12 @@ int vnext_conv3x3_tf32(const float *x, const float *weight_khwc, const float *bi
 /* dtype-generic form (see vnext_linear_tc): bf16 input needs Cin % 64 == 0, bf16 output Cout % 8 == 0. */
 int vnext_conv3x3_tc(int in_dtype, int out_dtype, const void *x, const void *weight_khwc, const float *bias, void *out,
                      int T, int H, int W, int Cin, int Cout, int relu, void *stream);
+/* ... with a stride: 1 or 2 (the stride-in-3x3 convs that open res3 / res4 / res5, detectron2/modeling/backbone/
+ * resnet.py:150-161 with STRIDE_IN_1X1 False, and the extra-level input projection, projects/SeqFormer/seqformer/models/
+ * deformable_detr.py:70-76).  H, W are the INPUT size; out is [T, (H-1)/stride+1, (W-1)/stride+1, Cout].  The strided
+ * taps are still single TMA boxes: the tensor map walks the input with element strides (stride, stride). */
+int vnext_conv3x3_strided_tc(int in_dtype, int out_dtype, const void *x, const void *weight_khwc, const float *bias,
+                             void *out, int T, int H, int W, int Cin, int Cout, int stride, int relu, void *stream);
 
 /*
  * Single-pass NHWC epilogues of the backbone / input projection (fp32, C % 4 == 0, 16-byte aligned):

@@ -83,6 +83,26 @@ def test_residual_relu_bias2d_and_row_mask():
     assert (out[mask.bool().repeat(M // S), :256] == 0).all()
 
 
+@pytest.mark.parametrize("T,H,W,Cin,Cout", [(2, 23, 40, 64, 64), (1, 8, 16, 64, 128), (3, 46, 80, 256, 256), (5, 184, 320, 128, 128),
+                                           (2, 13, 17, 128, 8), (1, 12, 20, 2048, 256), (2, 1, 1, 64, 64), (1, 7, 33, 64, 32)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conv3x3_stride2(T, H, W, Cin, Cout, dtype):
+    """The stride-in-3x3 convs (res3/res4/res5 openers, extra-level input projection): element-strided TMA boxes."""
+    from vnext_b200.linear import conv3x3
+    g = torch.Generator().manual_seed(T * 1000 + H)
+    x = torch.randn(T, H, W, Cin, generator=g).cuda().to(dtype)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5).cuda().to(dtype)
+    b = torch.randn(Cout, generator=g).cuda()
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), stride=2, padding=1).permute(0, 2, 3, 1)
+    out = conv3x3(x, wk, b, relu=False, stride=2)
+    assert out.shape == ref.shape
+    tol = (2e-3 if dtype == torch.float32 else 8e-3) * ref.abs().max().item()
+    assert (out.double() - ref).abs().max().item() < tol
+    out = conv3x3(x, wk, b, relu=True, stride=2)
+    assert (out.double() - ref.clamp(min=0)).abs().max().item() < tol
+
+
 @pytest.mark.parametrize("S,M", [(200, 1000), (136, 1000), (8, 300), (19560, 3 * 19560)])
 def test_periodic_bias2d_staged_by_tma(S, M):
     """period % 8 == 0: the row-periodic 2-D bias tile goes through shared memory as four 8-row TMA boxes (a 32-row tile may

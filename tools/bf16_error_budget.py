@@ -23,7 +23,7 @@ with torch.no_grad():
     ref = SO.inference(sd, frames)
 from vnext_b200.seqformer.engine import SeqFormerEngine  # noqa: E402
 
-for parts in ("", "backbone", "encoder", "backbone,encoder"):
+for parts in (sys.argv[2].split(";") if len(sys.argv) > 2 else ("", "backbone", "encoder", "backbone,encoder")):
     os.environ["VNEXT_BF16_PARTS"] = parts
     out = SeqFormerEngine(sd, device="cuda", precision="bf16").inference(torch.stack(frames).cuda())
     line = {}

@@ -183,7 +183,7 @@ struct GemmParams {
     // implicit-GEMM 3x3 convolution (stride 1, zero padding 1) over NHWC: the A tile of an 8 x 16 pixel patch and filter
     // tap (ky, kx) is ONE 4-D TMA box at (channel block, x0 + kx - 1, y0 + ky - 1, frame); out-of-image pixels are
     // zero-filled by the TMA unit, which is exactly the convolution's padding
-    int conv, conv_cin_blocks, conv_tiles_x, conv_tiles_y;
+    int conv, conv_cin_blocks, conv_tiles_x, conv_tiles_y, conv_stride;
     // cluster == 2: CTA pairs work on two vertically adjacent m-tiles of the same n-tile; each CTA loads half of the
     // weight (B) tile and multicasts it to both, halving the dominant L2 -> shared-memory operand traffic
     int cluster;
@@ -301,7 +301,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     const int tx = mt % p.conv_tiles_x, ty = (mt / p.conv_tiles_x) % p.conv_tiles_y;
                     const int fr = mt / (p.conv_tiles_x * p.conv_tiles_y);
                     const int tap = kb / p.conv_cin_blocks, cb = kb - tap * p.conv_cin_blocks;
-                    tma_load_4d(sa, &tmap_a, cb * BLOCK_K, tx * 16 + tap % 3 - 1, ty * 8 + tap / 3 - 1, fr, &full_bar[stage]);
+                    // stride s: the box starts at input pixel (s*x0 + kx - 1, s*y0 + ky - 1) and the tensor map steps by s
+                    tma_load_4d(sa, &tmap_a, cb * BLOCK_K, tx * 16 * p.conv_stride + tap % 3 - 1,
+                                ty * 8 * p.conv_stride + tap / 3 - 1, fr, &full_bar[stage]);
                 } else {
                     tma_load_2d(sa, &tmap_a, kb * BLOCK_K, m_idx, &full_bar[stage]);
                 }
@@ -605,7 +607,7 @@ static int make_tmap_2d(CUtensorMap *tm, int dt, const void *ptr, int rows, int 
 
 // 4-D NHWC tensor [T, H, W, C]; box = [1, box_h, box_w, box_c channels]
 static int make_tmap_nhwc(CUtensorMap *tm, int dt, const void *ptr, int T, int H, int W, int C, int box_h, int box_w,
-                          int box_c) {
+                          int box_c, int estride = 1) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled entry point not available");
@@ -614,8 +616,9 @@ static int make_tmap_nhwc(CUtensorMap *tm, int dt, const void *ptr, int T, int H
     const cuuint64_t esz = dt == VNEXT_BF16 ? 2 : 4;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T};
     cuuint64_t strides[3] = {(cuuint64_t)C * esz, (cuuint64_t)W * C * esz, (cuuint64_t)H * W * C * esz};
-    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
-    cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    // element strides (1, s, s, 1): a box of box_w*s x box_h*s input pixels delivers box_w x box_h of them
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)(box_w * estride), (cuuint32_t)(box_h * estride), 1u};
+    cuuint32_t estr[4] = {1u, (cuuint32_t)estride, (cuuint32_t)estride, 1u};
     CUresult r = enc(tm, dt == VNEXT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
                      const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      box_c * esz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -704,6 +707,7 @@ int linear_tc_device(const LinearArgs &x, cudaStream_t stream) {
     p.eps = x.eps;
     p.num_m_tiles = p.num_n_tiles = 0;
     p.conv = p.conv_cin_blocks = p.conv_tiles_x = p.conv_tiles_y = 0;
+    p.conv_stride = 1;
     p.cluster = 1;
     p.b2_tma = 0;
     p.vec_ok = al16(x.out) && x.ldo % oe == 0 && (!x.bias || al16(x.bias)) &&
@@ -754,10 +758,12 @@ int linear_tc_device(const LinearArgs &x, cudaStream_t stream) {
     return launch_any(wide, x.in_dt, x.out_dt, ta, tb, to, tr, p, stream);
 }
 
-int conv3x3_tc_device(int in_dt, int out_dt, const void *x, const void *w, const float *bias, void *out, int T, int H, int W,
-                      int Cin, int Cout, int relu, cudaStream_t stream) {
+int conv3x3_tc_device(int in_dt, int out_dt, const void *x, const void *w, const float *bias, void *out, int T, int Hin, int Win,
+                      int Cin, int Cout, int stride, int relu, cudaStream_t stream) {
     const int kbox = in_dt == VNEXT_BF16 ? 64 : 32;
+    const int H = (Hin - 1) / stride + 1, W = (Win - 1) / stride + 1;       // output size (kernel 3, padding 1)
     GemmParams p;
+    p.conv_stride = stride;
     p.M = T * H * W; p.N = Cout; p.K = 9 * Cin; p.bias = bias; p.bias2d = nullptr; p.period = 1; p.ldb2 = 0;
     p.b2_tma = 0;
     p.row_mask = nullptr; p.mask_cols = 0; p.residual = nullptr; p.gamma = p.beta = nullptr; p.out = static_cast<float *>(out);
@@ -773,7 +779,7 @@ int conv3x3_tc_device(int in_dt, int out_dt, const void *x, const void *w, const
         if (want == 2 && p.num_m_tiles * ((Cout + (wide ? 255 : 127)) / (wide ? 256 : 128)) >= 2 * num_sms()) p.cluster = 2;
     }
     CUtensorMap ta, tb, to;
-    int rc = make_tmap_nhwc(&ta, in_dt, x, T, H, W, Cin, 8, 16, kbox);
+    int rc = make_tmap_nhwc(&ta, in_dt, x, T, Hin, Win, Cin, 8, 16, kbox, stride);
     if (rc) return rc;
     rc = make_tmap_2d(&tb, in_dt, w, Cout, 9 * Cin, 9 * Cin, (wide ? 256 : 128) / p.cluster, kbox);
     if (rc) return rc;
@@ -787,7 +793,8 @@ int conv3x3_tc_device(int in_dt, int out_dt, const void *x, const void *w, const
 using namespace vnext;
 
 static int conv3x3_checked(const char *who, int in_dt, int out_dt, const void *x, const void *w, const float *bias, void *out,
-                           int T, int H, int W, int Cin, int Cout, int relu, void *stream) {
+                           int T, int H, int W, int Cin, int Cout, int stride, int relu, void *stream) {
+    VNEXT_CHECK_ARG(stride == 1 || stride == 2, "%s: stride must be 1 or 2 (got %d)", who, stride);
     VNEXT_CHECK_ARG((in_dt == VNEXT_F32 || in_dt == VNEXT_BF16) && (out_dt == VNEXT_F32 || out_dt == VNEXT_BF16),
                     "%s: dtypes must be fp32 (0) or bf16 (2)", who);
     VNEXT_CHECK_ARG(T >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "%s: bad shape", who);
@@ -796,17 +803,23 @@ static int conv3x3_checked(const char *who, int in_dt, int out_dt, const void *x
     if (T == 0) return VNEXT_OK;
     VNEXT_CHECK_ARG(x && w && out && al16(x) && al16(w) && al16(out) && (!bias || al16(bias)), "%s: null or unaligned pointer", who);
     VNEXT_CHECK_ARG((long long)T * H * W < (1ll << 31), "%s: too many pixels", who);
-    return conv3x3_tc_device(in_dt, out_dt, x, w, bias, out, T, H, W, Cin, Cout, relu, static_cast<cudaStream_t>(stream));
+    return conv3x3_tc_device(in_dt, out_dt, x, w, bias, out, T, H, W, Cin, Cout, stride, relu, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vnext_conv3x3_tf32(const float *x, const float *weight_khwc, const float *bias, float *out, int T, int H,
                                   int W, int Cin, int Cout, int relu, void *stream) {
-    return conv3x3_checked("vnext_conv3x3_tf32", VNEXT_F32, VNEXT_F32, x, weight_khwc, bias, out, T, H, W, Cin, Cout, relu, stream);
+    return conv3x3_checked("vnext_conv3x3_tf32", VNEXT_F32, VNEXT_F32, x, weight_khwc, bias, out, T, H, W, Cin, Cout, 1, relu, stream);
 }
 
 extern "C" int vnext_conv3x3_tc(int in_dtype, int out_dtype, const void *x, const void *weight_khwc, const float *bias,
                                 void *out, int T, int H, int W, int Cin, int Cout, int relu, void *stream) {
-    return conv3x3_checked("vnext_conv3x3_tc", in_dtype, out_dtype, x, weight_khwc, bias, out, T, H, W, Cin, Cout, relu, stream);
+    return conv3x3_checked("vnext_conv3x3_tc", in_dtype, out_dtype, x, weight_khwc, bias, out, T, H, W, Cin, Cout, 1, relu, stream);
+}
+
+extern "C" int vnext_conv3x3_strided_tc(int in_dtype, int out_dtype, const void *x, const void *weight_khwc, const float *bias,
+                                        void *out, int T, int H, int W, int Cin, int Cout, int stride, int relu, void *stream) {
+    return conv3x3_checked("vnext_conv3x3_strided_tc", in_dtype, out_dtype, x, weight_khwc, bias, out, T, H, W, Cin, Cout, stride,
+                           relu, stream);
 }
 
 static int linear_checked(const char *who, int in_dt, int out_dt, const void *a, int lda, const void *weight, const float *bias,

@@ -70,19 +70,21 @@ def linear(x, weight, bias=None, relu=False, gelu=False, residual=None, ln_weigh
     return out2.view(*x.shape[:-1], N) if out2.is_contiguous() else out2
 
 
-def conv3x3(x, weight_khwc, bias, relu=True, out_dtype=None):
-    """x [T,H,W,Cin] contiguous NHWC; weight_khwc [Cout, 9*Cin] (= conv weight.permute(0,2,3,1)); stride 1, padding 1.
+def conv3x3(x, weight_khwc, bias, relu=True, out_dtype=None, stride=1):
+    """x [T,H,W,Cin] contiguous NHWC; weight_khwc [Cout, 9*Cin] (= conv weight.permute(0,2,3,1)); stride 1 or 2, padding 1.
     x / weight fp32 (TF32 MMAs) or bf16; output dtype defaults to x's."""
     T, H, W, Cin = x.shape
     Cout = weight_khwc.shape[0]
     assert x.is_contiguous() and weight_khwc.is_contiguous() and x.dtype == weight_khwc.dtype
-    out = torch.empty((T, H, W, Cout), dtype=out_dtype or x.dtype, device=x.device)
-    info = {"flops": 2.0 * T * H * W * Cout * 9 * Cin,
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    out = torch.empty((T, Ho, Wo, Cout), dtype=out_dtype or x.dtype, device=x.device)
+    info = {"flops": 2.0 * T * Ho * Wo * Cout * 9 * Cin,
             "bytes": float(x.element_size() * (x.numel() + weight_khwc.numel()) + out.element_size() * out.numel())}
     tag = "tf32" if x.dtype == torch.float32 else "bf16"
     with torch.cuda.device(x.device):
-        rc = _cabi.timed_call(f"conv3x3_{tag}_c{Cin}_n{Cout}", info, x, lambda: _cabi.lib().vnext_conv3x3_tc(
+        rc = _cabi.timed_call(f"conv3x3_{tag}_c{Cin}_n{Cout}" + ("_s2" if stride == 2 else ""), info, x,
+                              lambda: _cabi.lib().vnext_conv3x3_strided_tc(
             _DT[x.dtype], _DT[out.dtype], x.data_ptr(), weight_khwc.data_ptr(), _ptr(bias), out.data_ptr(), T, H, W, Cin,
-            Cout, int(relu), torch.cuda.current_stream(x.device).cuda_stream))
-    _cabi.check(rc, "vnext_conv3x3_tc")
+            Cout, int(stride), int(relu), torch.cuda.current_stream(x.device).cuda_stream))
+    _cabi.check(rc, "vnext_conv3x3_strided_tc")
     return out

@@ -104,9 +104,11 @@ class SeqFormerEngine:
             raise RuntimeError("precision='bf16' exists only on the CUDA kernels")
         self.act_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
         import os
+        self._small_fp32 = os.environ.get("VNEXT_SMALL_FP32", "0") == "1"
         parts = os.environ.get("VNEXT_BF16_PARTS", "backbone,encoder").split(",")     # experiment switch (tools/bf16_error_budget.py)
         self.bb_dtype = self.act_dtype if "backbone" in parts else torch.float32      # backbone + input projection storage
-        self.enc_dtype = self.act_dtype if "encoder" in parts else torch.float32      # encoder value / sampled / FFN hidden
+        self.val_dtype = self.act_dtype if ("encoder" in parts or "value" in parts) else torch.float32    # MSDA value / sampled
+        self.hid_dtype = self.act_dtype if ("encoder" in parts or "hidden" in parts) else torch.float32   # FFN hidden
         self._plans: Dict[Tuple[int, int, int], ClipPlan] = {}
         self._khwc = {}
         self._wcast = {}
@@ -287,6 +289,20 @@ class SeqFormerEngine:
 
     def lin(self, x, wb, relu=False, residual=None, ln=None, gelu=False, **kw):
         """y = [relu]( [LayerNorm]( x W^T + b [+ residual] ) ) — one tcgen05 kernel when native."""
+        if self.native_gemm and self._small_fp32 and x.numel() // x.shape[-1] <= 4096:
+            # experiment switch (VNEXT_SMALL_FP32=1, tools/bf16_error_budget.py): exact-fp32 library GEMM for the 300-query
+            # decoder / heads, to measure how much of the TF32 modes' deviation comes from them
+            prev = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = False
+            y = F.linear(x.float(), wb[0], wb[1])
+            torch.backends.cuda.matmul.allow_tf32 = prev
+            if residual is not None:
+                y = y + residual
+            if ln is not None:
+                y = F.layer_norm(y, (y.shape[-1],), ln[0], ln[1], 1e-5)
+            if gelu:
+                y = F.gelu(y)
+            return F.relu(y) if relu else y
         if self.native_gemm:
             from ..linear import linear
             if residual is not None and residual.shape != x.shape[:-1] + (wb[0].shape[0],):
@@ -331,18 +347,18 @@ class SeqFormerEngine:
         return x.contiguous(memory_format=torch.channels_last)
 
     def _conv3x3_native(self, x_nhwc, wb, stride=1, relu=True):
-        """3x3 conv + folded-BN bias + ReLU.  Stride 1 with Cin % 32 == 0: implicit GEMM on tcgen05 (shifted 4-D TMA
-        boxes, fused epilogue).  Otherwise (the three stride-2 convs, fp32 parity mode): library conv without bias +
-        ONE fused bias/ReLU pass.  x_nhwc: [T,h,w,C] contiguous."""
+        """3x3 conv (stride 1 or 2) + folded-BN bias + ReLU.  Cin % 32 == 0 (64 for bf16): implicit GEMM on tcgen05 (shifted,
+        for stride 2 element-strided, 4-D TMA boxes; fused epilogue).  Otherwise (fp32 parity mode): library conv without
+        bias + ONE fused bias/ReLU pass.  x_nhwc: [T,h,w,C] contiguous."""
         from .. import fused
         cin, cout = wb[0].shape[1], wb[0].shape[0]
         bf = x_nhwc.dtype == torch.bfloat16
-        if self.native_gemm and stride == 1 and cin % (64 if bf else 32) == 0 and cout % (8 if bf else 4) == 0:
+        if self.native_gemm and stride in (1, 2) and cin % (64 if bf else 32) == 0 and cout % (8 if bf else 4) == 0:
             from ..linear import conv3x3
             key = (wb[0].data_ptr(), x_nhwc.dtype)
             if key not in self._khwc:              # [Cout, Cin, 3, 3] -> [Cout, (ky, kx, c)], once per weight
                 self._khwc[key] = wb[0].permute(0, 2, 3, 1).reshape(cout, 9 * cin).to(x_nhwc.dtype).contiguous()
-            return conv3x3(x_nhwc.contiguous(), self._khwc[key], wb[1], relu=relu)
+            return conv3x3(x_nhwc.contiguous(), self._khwc[key], wb[1], relu=relu, stride=stride)
         y = F.conv2d(x_nhwc.permute(0, 3, 1, 2), self._w(wb[0], x_nhwc.dtype, True), None, stride=stride,
                      padding=1).permute(0, 2, 3, 1)
         return fused.bias_act(y, wb[1], relu=relu, out=y)
@@ -380,6 +396,8 @@ class SeqFormerEngine:
             h, wd = plan.level_hw[l]
             if l < 3:
                 y = self.lin(feats[name], (w.reshape(self.C, -1), b)).reshape(T, h * wd, self.C)
+            elif self.native_gemm:       # extra level: 3x3 stride-2 conv on res5 (own implicit GEMM, bias fused)
+                y = self._conv3x3_native(feats[name], (w, b), stride=2, relu=False).reshape(T, h * wd, self.C)
             else:
                 xin = feats[name].permute(0, 3, 1, 2)
                 y = F.conv2d(xin, self._w(w, xin.dtype, True), self._w(b, xin.dtype), stride=2, padding=1).permute(0, 2, 3, 1)
@@ -423,7 +441,7 @@ class SeqFormerEngine:
     def _value(self, x, attn_w, plan):
         if self.native_gemm:      # padding rows zeroed in the GEMM epilogue
             kw = {"row_mask": plan.extra["mask_u8"], "mask_cols": self.C} if plan.any_pad else {}
-            v = self.lin(x, (attn_w["v_w"], attn_w["v_b"]), out_dtype=self.enc_dtype, **kw)
+            v = self.lin(x, (attn_w["v_w"], attn_w["v_b"]), out_dtype=self.val_dtype, **kw)
         else:
             v = F.linear(x, attn_w["v_w"], attn_w["v_b"])
             if plan.any_pad:
@@ -440,14 +458,40 @@ class SeqFormerEngine:
             s = self.sample(self._value(x, a, plan), oa, plan.enc_ref, plan, a["n_off"])
             if self.native_gemm:     # branch tensors in act_dtype (bf16 in bf16 mode), residual stream x in fp32
                 x = self.lin(s, (a["o_w"], a["o_b"]), residual=x, ln=w["norm1"], out_dtype=torch.float32)
-                h = self.lin(x, w["lin1"], relu=True, out_dtype=self.enc_dtype)
+                h = self.lin(x, w["lin1"], relu=True, out_dtype=self.hid_dtype)
                 x = self.lin(h, w["lin2"], residual=x, ln=w["norm2"], out_dtype=torch.float32)
             else:
                 x = self.lin(s, (a["o_w"], a["o_b"]), residual=x, ln=w["norm1"])
                 x = self.lin(self.lin(x, w["lin1"], relu=True), w["lin2"], residual=x, ln=w["norm2"])
         return x
 
-    def decoder(self, memory, plan, collect_all=False):
+    def memory_branches(self, memory, plan):
+        """Everything after the encoder that depends on `memory` only — the six decoder layers' value projections and
+        the mask branch (MaskHeadSmallConv) — enqueued on a SIDE stream: the decoder's own chain is ~100 launches of
+        3-48 CTAs on 300 queries (launch-latency bound, most SMs idle), these are full-chip GEMMs / convolutions that fill
+        the idle SMs meanwhile.  Works eagerly and under CUDA-graph capture (the side stream joins the capture through
+        the wait_stream fork/join).  -> {"values": [...], "value_events": [...], "feats": ..., "join": fn}; the caller
+        keeps the returned dict alive until the step's last kernel is enqueued (tensors allocated on the side stream)."""
+        if not self.native:
+            return None
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream(device=dev)
+        side = self._side_stream
+        side.wait_stream(main)
+        br = {"values": [], "value_events": []}
+        with torch.cuda.stream(side):
+            for w in self.dec:
+                br["values"].append(self._value(memory, w["attn"], plan))
+                ev = torch.cuda.Event()
+                ev.record(side)
+                br["value_events"].append(ev)
+            br["feats"] = self.mask_features(memory, plan)
+        br["join"] = lambda: main.wait_stream(side)
+        return br
+
+    def decoder(self, memory, plan, collect_all=False, branches=None):
         T, C = plan.T, self.C
         qpos = self.query_pos                                    # [1, nq, C]
         out = self.tgt                                           # [1, nq, C]
@@ -466,7 +510,12 @@ class SeqFormerEngine:
             out_box = self._mha(qb, out_box, w["self_attn_box"], residual=out_box, ln=w["norm2_box"])
             a = w["attn"]
             oa = self.lin(out_box + qpos, (a["oa_w"], a["oa_b"])).expand(T, -1, -1)
-            s = self.sample(self._value(memory, a, plan), oa, ref_in, plan, a["n_off"]).float()   # [T, nq, C]
+            if branches is not None:                             # projected on the side stream (memory_branches)
+                torch.cuda.current_stream(self.device).wait_event(branches["value_events"][lid])
+                value = branches["values"][lid]
+            else:
+                value = self._value(memory, a, plan)
+            s = self.sample(value, oa, ref_in, plan, a["n_off"]).float()   # [T, nq, C]
             t2 = self.lin(s, (a["o_w"], a["o_b"]))
             # tgt_box = norm1_box(tgt_box + output_proj_box(sampled)); broadcasts [1,nq,C] -> [T,nq,C] in layer 0
             out_box = self.lin(s, (a["ob_w"][C:], a["ob_b"][C:]), residual=out_box.expand(T, -1, -1), ln=w["norm1_box"])
@@ -624,9 +673,14 @@ class SeqFormerEngine:
         plan = self.plan(T, H, W)
         x = self.preprocess(frames, plan)
         memory = self.encoder(self.tokens(self.backbone(x), plan), plan)
-        levels = self.decoder(memory, plan, collect_all=all_levels)
+        br = self.memory_branches(memory, plan)
+        levels = self.decoder(memory, plan, collect_all=all_levels, branches=br)
         logits, boxes, params, ref_px = self.heads(levels[-1], plan)
-        feats = self.mask_features(memory, plan)
+        if br is not None:
+            br["join"]()
+            feats = br["feats"]
+        else:
+            feats = self.mask_features(memory, plan)
         masks = self.dynamic_masks(feats, params, ref_px)
         return {"pred_logits": logits, "pred_boxes": boxes.unsqueeze(0), "pred_masks": masks.unsqueeze(0),
                 "memory": memory, "image_size": (H, W)}
@@ -655,12 +709,17 @@ class SeqFormerEngine:
         ori_size = ori_size or (H, W)
         plan = self.plan(T, H, W)
         memory = self.encoder(self.tokens(feats, plan), plan)
-        level = self.decoder(memory, plan)[-1]
+        br = self.memory_branches(memory, plan)
+        level = self.decoder(memory, plan, branches=br)[-1]
         logits, boxes, params, ref_px = self.heads(level, plan)
         scores = logits[0].sigmoid()
         k = min(topk, scores.shape[0])
         _, idx = torch.topk(scores.max(1)[0], k=k)
-        feats = self.mask_features(memory, plan)
+        if br is not None:
+            br["join"]()
+            feats = br["feats"]
+        else:
+            feats = self.mask_features(memory, plan)
         if self.native:      # stride-8 logits -> boolean output masks in one pass (no stride-4 / full-res float tensors)
             from .. import fused
             l8 = self.mask_logits8(feats, params[idx], ref_px[:, idx])
@@ -682,11 +741,15 @@ class SeqFormerEngine:
         T, _, H, W = frames.shape
         plan = self.plan(T, H, W)
         memory = self.encoder(self.tokens(self.backbone(self.preprocess(frames, plan)), plan), plan)
-        level = self.decoder(memory, plan)[-1]
+        br = self.memory_branches(memory, plan)
+        level = self.decoder(memory, plan, branches=br)[-1]
         logits, boxes, params, ref_px = self.heads(level, plan)
         scores = logits[0].sigmoid()
         _, idx = torch.topk(scores.max(1)[0], k=min(topk, scores.shape[0]))
-        return scores[idx], self.dynamic_masks(self.mask_features(memory, plan), params[idx], ref_px[:, idx])
+        if br is not None:
+            br["join"]()
+        feats = br["feats"] if br is not None else self.mask_features(memory, plan)
+        return scores[idx], self.dynamic_masks(feats, params[idx], ref_px[:, idx])
 
     @staticmethod
     def finish_video(valid_scores, masks, ori_size, apply_cls_thres=0.05, multi_cls=True):
