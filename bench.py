@@ -499,6 +499,28 @@ def own_arm(args, rank, world, local_rank):
             if "msda_encoder" in roofline and tr.get("msda_encoder"):
                 roofline["msda_encoder"]["traffic"] = tr["msda_encoder"]
 
+    also_bf16 = None
+    if world == 1 and args.precision == "tf32" and swin is None and not args.no_gpu_baselines:
+        # the bf16 mode of the same model, device-resident, same timing discipline (reported, not the headline: its mask
+        # logits miss the 1e-2 parity bound, see config.precision)
+        m16 = SeqFormer(device=str(dev), precision="bf16")
+        m16.load_reference_state_dict(make_weights(0, None))
+        m16.eval()
+        r16 = m16.runner(T, H, W, (H, W))
+        r16.frames_dev.copy_(clip.to(dev))
+        for _ in range(3):
+            r16.run_device()
+        torch.cuda.synchronize()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record(r16.stream)
+        for _ in range(args.steps):
+            r16.run_device()
+        b1.record(r16.stream)
+        torch.cuda.synchronize()
+        ms16 = b0.elapsed_time(b1)
+        also_bf16 = {"precision": "bf16", "value": round(args.steps * T / (ms16 / 1e3), 2), "unit": "frames/s",
+                     "ms_per_step": round(ms16 / args.steps, 4)}
+        del m16, r16
     cpu = None
     if args.gpus == 1 and not args.no_cpu_baseline and swin is None:
         cfps, desc, cores, _, _ = cpu_oracle_fps(T, H, W, 1, 0, budget_s=20.0)
@@ -525,11 +547,15 @@ def own_arm(args, rank, world, local_rank):
                    "l2": "no flush: per-step working set (fp32 weights ~165 MB + activations > 1 GB) exceeds the 126 MB L2",
                    "parallelism": f"{world} independent replicas, no data-path collective",
                    "precision": {"fp32": "fp32 storage, fp32 (cuBLAS/cuDNN) GEMMs",
-                                 "tf32": "fp32 storage, TF32 tcgen05 GEMMs, fp32 accumulate",
-                                 "bf16": "bf16 storage + bf16 tcgen05 GEMMs through backbone / input projection / encoder / mask "
-                                         "branch, fp32 accumulate + statistics, fp32 sampling offsets/locations, fp32 (TF32) "
-                                         "300-query decoder; parity <= 1e-2 vs the fp32 oracle at this geometry "
-                                         "(tests/test_engine_gpu.py::test_full_size_parity_of_the_benchmarked_modes)"}[args.precision]},
+                                 "tf32": "fp32 storage, TF32 tcgen05 GEMMs / convs, fp32 accumulate; every dense output within 1e-2 "
+                                         "of its scale vs the fp32 CPU oracle AT THIS GEOMETRY (mask logits 6.2-6.6e-3, class "
+                                         "logits 1.8e-3, boxes 0.9e-3: tests/test_engine_gpu.py::"
+                                         "test_full_size_parity_of_the_benchmarked_modes)",
+                                 "bf16": "bf16 storage + bf16 tcgen05 GEMMs in the backbone / input projection and for the encoder's "
+                                         "value / sampled / FFN-hidden tensors; fp32 residual stream, accumulate and statistics, fp32 "
+                                         "sampling offsets/locations, TF32 300-query decoder and mask branch; class logits / boxes "
+                                         "within 1e-2 (2.5e-3 / 1.9e-3), mask logits 1.0-1.7e-2 of their scale (over the north "
+                                         "star's 1e-2: not the default mode), same test"}[args.precision]},
         "clocks": clocks,
         "e2e": {"value": round(e2e_fps, 2), "unit": "frames/s", "h2d_bytes_per_step": run.h2d_bytes,
                 "d2h_bytes_per_step": run.d2h_bytes, "instances_returned": len(res["pred_scores"]),
@@ -537,7 +563,7 @@ def own_arm(args, rank, world, local_rank):
                 "pipelined_value": round(e2e_stream_fps, 2),
                 "pipelined_api": "SeqFormer.stream(iterable): same inputs/outputs, 2 clips in flight"},
         "gpu_launches": int(launches_per_step * args.steps),
-        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "also": also,
+        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "also": also, "also_bf16": also_bf16,
         "stock_cuda_op": stock, "gpu_eager_baseline": eager,
     }
     print(json.dumps(line), flush=True)
@@ -684,7 +710,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="720p", choices=list(WORKLOADS))
-    ap.add_argument("--precision", default="bf16", choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--no-gpu-baselines", action="store_true", help="skip the stock-CUDA-op and eager-GPU comparator legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

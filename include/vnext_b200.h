@@ -197,6 +197,16 @@ int vnext_conv3x3_strided_tc(int in_dtype, int out_dtype, const void *x, const v
                              void *out, int T, int H, int W, int Cin, int Cout, int stride, int relu, void *stream);
 
 /*
+ * Multi-head self-attention over a few hundred queries (the decoder's object queries), head_dim 32:
+ *   out[b, i, h*32 + c] = sum_j softmax_j(q_i . k_j / sqrt(32)) v_j[c]   per (batch b, head h)
+ * with q | k | v read in place from the merged in-projection qkv [batch, n, >= 3*heads*32] (row pitch ld floats: q at
+ * column 0, k at heads*32, v at 2*heads*32).  Replaces what nn.MultiheadAttention runs after its in-projection
+ * (projects/SeqFormer/seqformer/models/deformable_transformer.py:280-298; scale, head split, two bmm, softmax, merge).
+ * n <= 512.  fp32.
+ */
+int vnext_mha_small(const float *qkv, int ld, float *out, int ldo, int batch, int n, int heads, void *stream);
+
+/*
  * Single-pass NHWC epilogues of the backbone / input projection (fp32, C % 4 == 0, 16-byte aligned):
  *   vnext_bias_act      out = act(x + bias[c] (+ residual))      — folded FrozenBN bias + ReLU (+ shortcut) after a
  *                       library conv (detectron2/modeling/backbone/resnet.py:194-210; layers/batch_norm.py:44-65)

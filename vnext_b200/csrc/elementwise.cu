@@ -101,24 +101,44 @@ __global__ void __launch_bounds__(kGnThreads) groupnorm_partial_kernel(const IT 
     }
 }
 
-// stats[n][g] = (mean, rstd): blocks folded in index order, Chan et al. pairwise update in double precision.
+// stats[n][g] = (mean, rstd).  One WARP per (n, group): lane l folds blocks l, l+32, ... in index order, then the 32
+// partial (count, mean, M2) triples are merged by a fixed xor-shuffle tree — Chan et al.'s pairwise update in double
+// precision at every step, so the order of operations is a function of (nblk, HW) only: deterministic, and 30x
+// shorter than the serial fold over all blocks it replaces (that loop cost ~40 us per level at 720p).
+__device__ __forceinline__ void chan_merge(double &cnt, double &mean, double &m2, double cb, double mb, double m2b) {
+    if (cb == 0.0) return;
+    const double tot = cnt + cb, delta = mb - mean;
+    m2 += m2b + delta * delta * cnt * cb / tot;
+    mean += delta * cb / tot;
+    cnt = tot;
+}
 __global__ void groupnorm_combine_kernel(const float *__restrict__ part, float *__restrict__ stats, int nblk, int HW, int G,
                                          float eps) {
-    const int n = blockIdx.x, g = threadIdx.x;
+    const int n = blockIdx.x, g = blockIdx.y * 32 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (g >= G) return;
     double cnt = 0.0, mean = 0.0, m2 = 0.0;
-    for (int b = 0; b < nblk; ++b) {
+    for (int b = lane; b < nblk; b += 32) {
         const float *p = part + (((long long)n * nblk + b) * G + g) * 2;
         const double cb = 8.0 * (double)min(kGnRowsPerCta, HW - b * kGnRowsPerCta);
         const double sb = (double)p[0], mb = sb / cb;
-        const double m2b = fmax((double)p[1] - sb * mb, 0.0);
-        const double tot = cnt + cb, delta = mb - mean;
-        m2 += m2b + delta * delta * cnt * cb / tot;
-        mean += delta * cb / tot;
-        cnt = tot;
+        chan_merge(cnt, mean, m2, cb, mb, fmax((double)p[1] - sb * mb, 0.0));
     }
-    stats[((long long)n * G + g) * 2] = (float)mean;
-    stats[((long long)n * G + g) * 2 + 1] = (float)(1.0 / sqrt(m2 / cnt + (double)eps));
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {          // lower lane's triple first: the same association on every replay
+        const double oc = __shfl_xor_sync(0xffffffffu, cnt, o), om = __shfl_xor_sync(0xffffffffu, mean, o),
+                     o2 = __shfl_xor_sync(0xffffffffu, m2, o);
+        if (lane & o) {
+            double c2 = oc, mm = om, q2 = o2;
+            chan_merge(c2, mm, q2, cnt, mean, m2);
+            cnt = c2; mean = mm; m2 = q2;
+        } else {
+            chan_merge(cnt, mean, m2, oc, om, o2);
+        }
+    }
+    if (lane == 0) {
+        stats[((long long)n * G + g) * 2] = (float)mean;
+        stats[((long long)n * G + g) * 2 + 1] = (float)(1.0 / sqrt(m2 / cnt + (double)eps));
+    }
 }
 
 template <typename IT, typename OT>
@@ -184,7 +204,7 @@ static void groupnorm_launch(const void *x, const float *gamma, const float *bet
     float *part = stats_ws + (size_t)N * groups * 2;          // [N][nblk][G][2] after the [N][G][2] (mean, rstd) table
     dim3 grid(nblk, N);
     groupnorm_partial_kernel<IT><<<grid, kGnThreads, 0, st>>>((const IT *)x, part, HW, C);
-    groupnorm_combine_kernel<<<N, ((groups + 31) / 32) * 32, 0, st>>>(part, stats_ws, nblk, HW, groups, eps);
+    groupnorm_combine_kernel<<<dim3(N, (groups + 31) / 32), 1024, 0, st>>>(part, stats_ws, nblk, HW, groups, eps);
     const long long total = (long long)N * HW * (C / 4);
     groupnorm_apply_kernel<IT, OT><<<grid_for(total, 256), 256, 0, st>>>((const IT *)x, stats_ws, (const float4 *)gamma,
                                                                        (const float4 *)beta, (OT *)out, N, HW, C,

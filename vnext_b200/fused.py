@@ -103,6 +103,19 @@ def swin_window_attention(qkv, qkv_bias, table, heads, window, shift, tensor_cor
     return out
 
 
+def small_mha(qkv, heads):
+    """qkv [B, n, 3*heads*32] fp32 (rows may be strided) -> softmax(q k^T / sqrt(32)) v, heads merged: [B, n, heads*32]."""
+    B, n, C3 = qkv.shape
+    C = heads * 32
+    assert C3 >= 3 * C and qkv.dtype == torch.float32 and qkv.stride(2) == 1 and qkv.stride(0) == n * qkv.stride(1)
+    out = torch.empty((B, n, C), dtype=torch.float32, device=qkv.device)
+    info = {"bytes": 4.0 * (qkv.numel() + out.numel()), "flops": 4.0 * B * heads * n * n * 32}
+    rc = _cabi.timed_call("mha_small", info, qkv, lambda: _cabi.lib().vnext_mha_small(
+        qkv.data_ptr(), qkv.stride(1), out.data_ptr(), C, B, n, heads, _st(qkv)))
+    _cabi.check(rc, "vnext_mha_small")
+    return out
+
+
 def dynamic_mask_head(feats_nhwc, params, ref_px, stride=8):
     """feats_nhwc [T,H,W,8]; params [n,169] or [T,n,169]; ref_px [T,n,2] -> stride-8 logits [n,T,H,W]."""
     T, H, W, C = feats_nhwc.shape

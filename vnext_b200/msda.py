@@ -58,13 +58,15 @@ def _check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_w
 # ---------------------------------------------------------------- self-attention (encoder shape) kernels
 # When the queries are the pixel grid (Lq == S: encoder self-attention) two more kernels exist besides the tile kernel,
 # both exact for ANY sampling locations (include/vnext_b200.h: vnext_msda_forward_selfattn):
-#   "cached": cache-blocked (csrc/msda_cached.cu) — 2-D query tiles x one head per work unit, 32 warps/SM, the L1 keeps
-#             what neighbouring queries share (the tile kernel re-fetches it from L2: 5 GB of L2 sectors per 720p launch);
+#   "cached": cache-blocked (csrc/msda_cached.cu; DEFAULT) — 2-D query tiles x one head per work unit, 32 warps/SM, the L1
+#             keeps what neighbouring queries share (the tile kernel re-fetches it from L2: 5 GB of L2 sectors per 720p
+#             launch, 1 GB here).  Never slower than the tile kernel over profiles/r02_msda_encoder_kernels.jsonl (8 shapes
+#             incl. uniformly random locations): 352 vs 387 us fp32, 295 vs 309 us bf16 value at 720p x 5 frames;
 #   "auto":   shared-memory windows staged by TMA (csrc/msda_window.cu).  Removes the L2 traffic too, but at 16 warps/SM it
 #             is bound by shared-memory wavefronts / issue slots: 433 us (bf16 value) / 600 us (fp32) at 720p against
 #             311 / 387 us for the tile kernel (profiles/r02_msda_window_*): kept as an opt-in;
 #   "off":    always the tile kernel.
-WINDOW_MODE = "off"
+WINDOW_MODE = "cached"
 WINDOW_MARGIN = {torch.float32: 4, torch.bfloat16: 6}      # pixels around the tile footprint staged per level
 
 

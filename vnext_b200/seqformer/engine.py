@@ -107,9 +107,12 @@ class SeqFormerEngine:
         self._small_fp32 = os.environ.get("VNEXT_SMALL_FP32", "0") == "1"
         parts = os.environ.get("VNEXT_BF16_PARTS", "backbone,encoder").split(",")     # experiment switch (tools/bf16_error_budget.py)
         self.bb_dtype = self.act_dtype if "backbone" in parts else torch.float32      # backbone + input projection storage
+        if swin is not None:
+            self.bb_dtype = torch.float32      # the Swin kernels (window attention, row LayerNorm) are fp32 / TF32 only
         self.val_dtype = self.act_dtype if ("encoder" in parts or "value" in parts) else torch.float32    # MSDA value / sampled
         self.hid_dtype = self.act_dtype if ("encoder" in parts or "hidden" in parts) else torch.float32   # FFN hidden
         self._plans: Dict[Tuple[int, int, int], ClipPlan] = {}
+        self._qpb = {}
         self._khwc = {}
         self._wcast = {}
         sd = state_dict
@@ -289,7 +292,7 @@ class SeqFormerEngine:
 
     def lin(self, x, wb, relu=False, residual=None, ln=None, gelu=False, **kw):
         """y = [relu]( [LayerNorm]( x W^T + b [+ residual] ) ) — one tcgen05 kernel when native."""
-        if self.native_gemm and self._small_fp32 and x.numel() // x.shape[-1] <= 4096:
+        if self.native_gemm and self._small_fp32 and x.numel() // x.shape[-1] <= 4096 and "bias2d" not in kw:
             # experiment switch (VNEXT_SMALL_FP32=1, tools/bf16_error_budget.py): exact-fp32 library GEMM for the 300-query
             # decoder / heads, to measure how much of the TF32 modes' deviation comes from them
             prev = torch.backends.cuda.matmul.allow_tf32
@@ -317,6 +320,29 @@ class SeqFormerEngine:
         if gelu:
             y = F.gelu(y)
         return F.relu(y) if relu else y
+
+    def _qpos_bias(self, key, weight, bias, qk_rows=None):
+        """(x + query_pos) W^T + b  ==  x W^T + (query_pos W^T + b): the query-position share of a decoder projection, once per
+        weight (exact fp32), consumed as a row-periodic 2-D bias [nq, N] by the GEMM epilogue.  qk_rows: only the first
+        qk_rows output rows see query_pos (the q | k part of a merged q | k | v in-projection; v projects x alone)."""
+        if key not in self._qpb:
+            prev = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = False
+            pb = F.linear(self.query_pos[0], weight, bias)                       # [nq, N]
+            if qk_rows is not None:
+                pb[:, qk_rows:] = bias[qk_rows:]
+            torch.backends.cuda.matmul.allow_tf32 = prev
+            self._qpb[key] = pb.contiguous()
+        return self._qpb[key]
+
+    def _mha_self(self, x, w, key, ln):
+        """LN(x + nn.MultiheadAttention(q = k = x + query_pos, v = x)) on our kernels: ONE merged q | k | v projection
+        (query_pos folded into a 2-D bias), ONE attention kernel (csrc/small_attention.cu), out-projection + residual + LN."""
+        from .. import fused
+        in_w, in_b, out_w, out_b = w
+        qkv = self.lin(x, (in_w, None), bias2d=self._qpos_bias(key, in_w, in_b, qk_rows=2 * self.C))     # [B, nq, 3C]
+        o = fused.small_mha(qkv.float() if qkv.dtype != torch.float32 else qkv, self.M)
+        return self.lin(o, (out_w, out_b), residual=x, ln=ln)
 
     def _mha(self, q_in, v_in, w, residual=None, ln=None):
         """LN(residual + nn.MultiheadAttention(q=k=q_in, v=v_in)), batch-first [B, n, C]."""
@@ -504,12 +530,18 @@ class SeqFormerEngine:
                 ref_in = ref[:, :, None] * torch.cat([vr, vr], -1)[:, None]
             else:
                 ref_in = ref[:, :, None] * vr[:, None]
-            q = out + qpos
-            out = self._mha(q, out, w["self_attn"], residual=out, ln=w["norm2"])
-            qb = out_box + qpos
-            out_box = self._mha(qb, out_box, w["self_attn_box"], residual=out_box, ln=w["norm2_box"])
             a = w["attn"]
-            oa = self.lin(out_box + qpos, (a["oa_w"], a["oa_b"])).expand(T, -1, -1)
+            if self.native_gemm and out.dtype == torch.float32:
+                out = self._mha_self(out, w["self_attn"], (lid, "sa"), w["norm2"])
+                out_box = self._mha_self(out_box, w["self_attn_box"], (lid, "sab"), w["norm2_box"])
+                oa = self.lin(out_box, (a["oa_w"], None), bias2d=self._qpos_bias((lid, "oa"), a["oa_w"], a["oa_b"]))
+                oa = oa.expand(T, -1, -1)
+            else:
+                q = out + qpos
+                out = self._mha(q, out, w["self_attn"], residual=out, ln=w["norm2"])
+                qb = out_box + qpos
+                out_box = self._mha(qb, out_box, w["self_attn_box"], residual=out_box, ln=w["norm2_box"])
+                oa = self.lin(out_box + qpos, (a["oa_w"], a["oa_b"])).expand(T, -1, -1)
             if branches is not None:                             # projected on the side stream (memory_branches)
                 torch.cuda.current_stream(self.device).wait_event(branches["value_events"][lid])
                 value = branches["values"][lid]
