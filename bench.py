@@ -334,6 +334,10 @@ def own_arm(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        # one process per GPU on ONE host: without a cap every rank spins up cpu_count intra-op threads for its host-side
+        # staging copies and the ranks oversubscribe each other (end-to-end efficiency 0.76 at 8 GPUs in round 1)
+        torch.set_num_threads(max(1, min(16, (os.cpu_count() or world) // world)))
     T, H, W = WORKLOADS[args.workload]
     swin = None
     if args.workload.startswith("swinl"):           # BASELINE config 4's backbone (tf32 here; bf16 is a later round)

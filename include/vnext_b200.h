@@ -202,9 +202,21 @@ int vnext_conv3x3_strided_tc(int in_dtype, int out_dtype, const void *x, const v
  * with q | k | v read in place from the merged in-projection qkv [batch, n, >= 3*heads*32] (row pitch ld floats: q at
  * column 0, k at heads*32, v at 2*heads*32).  Replaces what nn.MultiheadAttention runs after its in-projection
  * (projects/SeqFormer/seqformer/models/deformable_transformer.py:280-298; scale, head split, two bmm, softmax, merge).
- * n <= 512.  fp32.
+ * n <= 384.  fp32.
  */
 int vnext_mha_small(const float *qkv, int ld, float *out, int ldo, int batch, int n, int heads, void *stream);
+
+/*
+ * Small fused pieces of the SeqFormer decoder layer (fp32, 300 queries x T frames):
+ *   vnext_time_pool_ln  out[q,:] = LayerNorm(out_in[q,:] + sum_t softmax_t(logit[t,q]) * t2[t,q,:]) — temporal pooling of the
+ *                       per-frame samples into the clip-level query (projects/SeqFormer/seqformer/models/
+ *                       deformable_transformer.py:314-317).  t2 [T,nq,C], logit [T,nq], out_in / out [nq,C]; T <= 64, C <= 256.
+ *   vnext_box_refine    out[r,0:4] = sigmoid(delta[r,:] + pad(inverse_sigmoid(ref[r,0:ref_dim]))) — iterative box refinement
+ *                       (deformable_transformer.py:366-377; inverse_sigmoid eps 1e-5); ref_dim 2 or 4; rows = T * nq.
+ */
+int vnext_time_pool_ln(const float *out_in, const float *t2, const float *logit, const float *gamma, const float *beta,
+                       float *out, int T, int nq, int C, float eps, void *stream);
+int vnext_box_refine(const float *delta, const float *ref, float *out, int rows, int ref_dim, void *stream);
 
 /*
  * Single-pass NHWC epilogues of the backbone / input projection (fp32, C % 4 == 0, 16-byte aligned):

@@ -40,8 +40,11 @@ def main():
     ap.add_argument("--swin", choices=["T", "L"], default=None, help="Swin backbone instead of ResNet-50")
     ap.add_argument("--num-queries", type=int, default=300)
     ap.add_argument("--num-classes", type=int, default=40)
+    ap.add_argument("--unsafe-pickle", action="store_true",
+                    help="allow arbitrary pickled objects (legacy model-zoo files); only for checkpoints you trust")
     args = ap.parse_args()
-    obj = torch.load(args.checkpoint, map_location="cpu", weights_only=False)
+    # a validation tool must not execute code from the file it validates: tensors-only unpickling unless asked otherwise
+    obj = torch.load(args.checkpoint, map_location="cpu", weights_only=not args.unsafe_pickle)
     sd = obj.get("model", obj) if isinstance(obj, dict) else obj
     swin = {"T": dict(SWIN_T), "L": dict(SWIN_L)}.get(args.swin)
     fn = seqformer_r50_state_spec if args.arch == "seqformer" else idol_r50_state_spec

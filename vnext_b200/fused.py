@@ -103,6 +103,29 @@ def swin_window_attention(qkv, qkv_bias, table, heads, window, shift, tensor_cor
     return out
 
 
+def time_pool_ln(out_in, t2, logit, gamma, beta, eps=1e-5):
+    """out_in [1,nq,C], t2 [T,nq,C], logit [T,nq,1] -> LayerNorm(out_in + sum_t softmax_t(logit) t2) [1,nq,C] (fp32)."""
+    T, nq, C = t2.shape
+    assert out_in.is_contiguous() and t2.is_contiguous() and logit.is_contiguous() and t2.dtype == torch.float32
+    out = torch.empty_like(out_in)
+    rc = _cabi.timed_call("time_pool_ln", {"bytes": 4.0 * (t2.numel() + 2 * out.numel())}, t2, lambda: _cabi.lib().vnext_time_pool_ln(
+        out_in.data_ptr(), t2.data_ptr(), logit.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), T, nq, C,
+        float(eps), _st(t2)))
+    _cabi.check(rc, "vnext_time_pool_ln")
+    return out
+
+
+def box_refine(delta, ref):
+    """delta [..., 4], ref [..., 2|4] (same leading shape) -> sigmoid(delta + pad(inverse_sigmoid(ref))) [..., 4]."""
+    delta, ref = delta.contiguous(), ref.contiguous()
+    out = torch.empty_like(delta)
+    rows = delta.numel() // 4
+    rc = _cabi.timed_call("box_refine", {"bytes": 4.0 * (2 * delta.numel() + ref.numel())}, delta, lambda: _cabi.lib().vnext_box_refine(
+        delta.data_ptr(), ref.data_ptr(), out.data_ptr(), rows, ref.shape[-1], _st(delta)))
+    _cabi.check(rc, "vnext_box_refine")
+    return out
+
+
 def small_mha(qkv, heads):
     """qkv [B, n, 3*heads*32] fp32 (rows may be strided) -> softmax(q k^T / sqrt(32)) v, heads merged: [B, n, heads*32]."""
     B, n, C3 = qkv.shape

@@ -379,7 +379,13 @@ class SeqFormerEngine:
         from .. import fused
         cin, cout = wb[0].shape[1], wb[0].shape[0]
         bf = x_nhwc.dtype == torch.bfloat16
-        if self.native_gemm and stride in (1, 2) and cin % (64 if bf else 32) == 0 and cout % (8 if bf else 4) == 0:
+        T_, h_, w_ = x_nhwc.shape[:3]
+        m_tiles = T_ * (-(-((h_ - 1) // stride + 1) // 8)) * (-(-((w_ - 1) // stride + 1) // 16))
+        # few output tiles x a long K loop (the extra-level projection: 2048 -> 256 on a 12x20 map, 20 tiles, K = 18432) would
+        # run on 20 SMs for 280 us: that shape needs split-K, which the implicit-GEMM kernel does not have -> library conv
+        enough = m_tiles * (-(-cout // 256)) >= 48 or 9 * cin <= 4608
+        if (self.native_gemm and stride in (1, 2) and cin % (64 if bf else 32) == 0 and cout % (8 if bf else 4) == 0
+                and enough):
             from ..linear import conv3x3
             key = (wb[0].data_ptr(), x_nhwc.dtype)
             if key not in self._khwc:              # [Cout, Cin, 3, 3] -> [Cout, (ky, kx, c)], once per weight
@@ -553,14 +559,22 @@ class SeqFormerEngine:
             out_box = self.lin(s, (a["ob_w"][C:], a["ob_b"][C:]), residual=out_box.expand(T, -1, -1), ln=w["norm1_box"])
             out_box = self.lin(self.lin(out_box, w["linear1_box"], relu=True), w["linear2_box"], residual=out_box,
                                ln=w["norm3_box"])
-            tw = torch.softmax(self.lin(out_box, w["time_attention_weights"]), 0)
-            out = self._ln(out + (t2 * tw).sum(0, keepdim=True), w["norm1"])
+            if self.native_gemm and t2.dtype == torch.float32:
+                from .. import fused
+                out = fused.time_pool_ln(out.contiguous(), t2.contiguous(),
+                                         self.lin(out_box, w["time_attention_weights"]).contiguous(), *w["norm1"])
+            else:
+                tw = torch.softmax(self.lin(out_box, w["time_attention_weights"]), 0)
+                out = self._ln(out + (t2 * tw).sum(0, keepdim=True), w["norm1"])
             out = self.lin(self.lin(out, w["linear1"], relu=True), w["linear2"], residual=out, ln=w["norm3"])
             tmp = out_box
             for j, wb in enumerate(w["bbox"]):
                 tmp = self.lin(tmp, wb, relu=(j < 2))
             prev_ref = ref
-            if ref.shape[-1] == 4:
+            if self.native_gemm and tmp.dtype == torch.float32:
+                from .. import fused
+                ref = fused.box_refine(tmp, ref)
+            elif ref.shape[-1] == 4:
                 ref = (tmp + inverse_sigmoid(ref)).sigmoid()
             else:
                 ref = torch.cat([tmp[..., :2] + inverse_sigmoid(ref), tmp[..., 2:]], -1).sigmoid()
