@@ -270,6 +270,12 @@ int vnext_swin_window_attention_tc(const float *qkv, const float *qkv_bias, cons
                                    int B, int H, int W, int C, int heads, int window, int shift, void *stream);
 int vnext_layernorm(const float *x, const float *gamma, const float *beta, float *out, long long rows, int C,
                     float eps, void *stream);
+/* dtype-generic forms (VNEXT_F32 / VNEXT_BF16 storage; TF32 MMAs, fp32 statistics): the bf16 mode of the Swin backbone keeps
+ * its residual stream in fp32 and hands bf16 tensors to / takes them from the bf16 GEMMs. */
+int vnext_swin_window_attention_tc_dt(int io_dtype, const void *qkv, const float *qkv_bias, const float *rel_pos_bias_table,
+                                      void *out, int B, int H, int W, int C, int heads, int window, int shift, void *stream);
+int vnext_layernorm_dt(int in_dtype, int out_dtype, const void *x, const float *gamma, const float *beta, void *out,
+                       long long rows, int C, float eps, void *stream);
 
 /*
  * Fused AdamW over a flat fp32 segment (training step; torch.optim.AdamW semantics as built by

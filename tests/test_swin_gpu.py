@@ -35,6 +35,12 @@ def test_window_attention_kernel(B, H, W, heads, ws, shift):
     if ws >= 4:           # tensor-core (TF32) variant: same contract, TF32 tolerance
         tc = fused.swin_window_attention(qkv, bias, table, heads, ws, shift, tensor_cores=True)
         assert (tc.double() - want).abs().max().item() < 5e-3 * max(1.0, want.abs().max().item())
+        # bf16 storage of qkv / out (the Swin bf16 mode): same kernel, operands widened in the gather
+        q16 = qkv.bfloat16()
+        want16 = _window_attention_torch(q16.double(), bias.double(), table.double(), heads, ws, shift)
+        tc16 = fused.swin_window_attention(q16, bias, table, heads, ws, shift, tensor_cores=True)
+        assert tc16.dtype == torch.bfloat16
+        assert (tc16.double() - want16).abs().max().item() < 1.2e-2 * max(1.0, want16.abs().max().item())
 
 
 def test_layernorm_and_gelu_epilogue():
@@ -46,6 +52,11 @@ def test_layernorm_and_gelu_epilogue():
         w, b = (torch.rand(C, generator=g) + 0.5).cuda(), torch.randn(C, generator=g).cuda()
         want = F.layer_norm(x.double(), (C,), w.double(), b.double(), 1e-5)
         assert (fused.layernorm(x, w, b).double() - want).abs().max().item() < 1e-4
+        o16 = fused.layernorm(x, w, b, out_dtype=torch.bfloat16)                       # fp32 stream -> bf16 GEMM operand
+        assert o16.dtype == torch.bfloat16 and (o16.double() - want).abs().max().item() < 8e-3 * want.abs().max().item()
+        x16 = x.bfloat16()
+        want16 = F.layer_norm(x16.double(), (C,), w.double(), b.double(), 1e-5)
+        assert (fused.layernorm(x16, w, b, out_dtype=torch.float32).double() - want16).abs().max().item() < 1e-4
     x = torch.randn(1000, 192, generator=g).cuda()
     w = (torch.randn(768, 192, generator=g) / 14).cuda()
     b = torch.randn(768, generator=g).cuda()
@@ -53,7 +64,7 @@ def test_layernorm_and_gelu_epilogue():
     assert (linear(x, w, b, gelu=True).double() - want).abs().max().item() < 5e-3     # TF32 operands
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("tf32", 3e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("tf32", 3e-2), ("bf16", 5e-2)])
 def test_swin_backbone_and_engines(precision, tol):
     from vnext_b200.idol.engine import IDOLEngine
     from vnext_b200.idol.state_spec import idol_r50_state_spec

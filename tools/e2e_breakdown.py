@@ -68,11 +68,26 @@ def main():
         res = model(batched)                      # as bench.py does: the previous clip's result stays alive during the call
     torch.cuda.synchronize()
     whole_retain = (time.perf_counter() - t0) * 1e3 / n
+    import gc
+    events = []
+    gc.callbacks.append(lambda phase, info: events.append((phase, info.get("generation"), time.perf_counter())))
     per_call = []
-    for _ in range(6):
+    for _ in range(24):
         t1 = time.perf_counter()
         res = model(batched)
         per_call.append(round((time.perf_counter() - t1) * 1e3, 2))
+    gc_starts = [(g, t) for ph, g, t in events if ph == "start"]
+    gc_stops = [(g, t) for ph, g, t in events if ph == "stop"]
+    gc_ms = [(g0, round((t1_ - t0_) * 1e3, 2)) for (g0, t0_), (_, t1_) in zip(gc_starts, gc_stops)]
+    gc.callbacks.clear()
+    gc.collect()
+    gc.freeze()
+    frozen = []
+    for _ in range(24):
+        t1 = time.perf_counter()
+        res = model(batched)
+        frozen.append(round((time.perf_counter() - t1) * 1e3, 2))
+    print(json.dumps({"gc_collections_during_24_calls (generation, ms)": gc_ms, "per_call_ms_after_gc_freeze": frozen}))
     print(json.dumps({"precision": precision, "forward_call_retaining_previous_result_ms": round(whole_retain, 3),
                       "per_call_ms": per_call, "per_stage_ms": {k: round(v / n, 3) for k, v in acc.items()},
                       "sum_ms": round(sum(acc.values()) / n, 3), "forward_call_ms": round(whole, 3),

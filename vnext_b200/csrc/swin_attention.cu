@@ -164,19 +164,21 @@ __global__ void __launch_bounds__(kWinThreads, 2) swin_window_attention_kernel(c
     }
 }
 
-// Row LayerNorm: one warp per row, C % 4 == 0, two passes over registers (C <= 32 * 4 * kLnVec).
+// Row LayerNorm: one warp per row, C % 4 == 0, two passes over the row (C <= 32 * 4 * kLnVec).  IT / OT: fp32 or bf16
+// storage of x / out (statistics and affine parameters fp32).
 constexpr int kLnVec = 48;      // float4 per lane: C up to 6144
-__global__ void __launch_bounds__(256) layernorm_rows_kernel(const float4 *__restrict__ x, const float4 *__restrict__ gamma,
-                                                             const float4 *__restrict__ beta, float4 *__restrict__ out,
+template <typename IT, typename OT>
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const IT *__restrict__ x, const float4 *__restrict__ gamma,
+                                                             const float4 *__restrict__ beta, OT *__restrict__ out,
                                                              long long rows, int c4, float eps) {
     const int lane = threadIdx.x & 31;
     const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long row = warp0; row < rows; row += nwarps) {
-        const float4 *xr = x + row * c4;
+        const IT *xr = x + row * c4 * 4;
         float sum = 0.f, sumsq = 0.f;
         for (int i = lane; i < c4; i += 32) {
-            const float4 v = xr[i];
+            const float4 v = load4(xr + i * 4);
             sum += (v.x + v.y) + (v.z + v.w);
             sumsq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
         }
@@ -188,11 +190,11 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float4 *__res
         const float inv_n = 1.f / (4.f * c4);
         const float mean = sum * inv_n;
         const float rstd = rsqrtf(fmaxf(sumsq * inv_n - mean * mean, 0.f) + eps);
-        float4 *orow = out + row * c4;
+        OT *orow = out + row * c4 * 4;
         for (int i = lane; i < c4; i += 32) {
-            const float4 v = xr[i], g = __ldg(gamma + i), b = __ldg(beta + i);
-            orow[i] = make_float4((v.x - mean) * rstd * g.x + b.x, (v.y - mean) * rstd * g.y + b.y,
-                                  (v.z - mean) * rstd * g.z + b.z, (v.w - mean) * rstd * g.w + b.w);
+            const float4 v = load4(xr + i * 4), g = __ldg(gamma + i), b = __ldg(beta + i);
+            store4(orow + i * 4, make_float4((v.x - mean) * rstd * g.x + b.x, (v.y - mean) * rstd * g.y + b.y,
+                                             (v.z - mean) * rstd * g.z + b.z, (v.w - mean) * rstd * g.w + b.w));
         }
     }
 }
@@ -231,19 +233,34 @@ int vnext_swin_window_attention(const float *qkv, const float *qkv_bias, const f
     return VNEXT_OK;
 }
 
-int vnext_layernorm(const float *x, const float *gamma, const float *beta, float *out, long long rows, int C, float eps,
-                    void *stream) {
+int vnext_layernorm_dt(int in_dtype, int out_dtype, const void *x, const float *gamma, const float *beta, void *out, long long rows,
+                       int C, float eps, void *stream) {
+    VNEXT_CHECK_ARG((in_dtype == VNEXT_F32 || in_dtype == VNEXT_BF16) && (out_dtype == VNEXT_F32 || out_dtype == VNEXT_BF16),
+                    "vnext_layernorm: dtypes must be fp32 (0) or bf16 (2)");
     VNEXT_CHECK_ARG(rows >= 0 && C > 0 && C % 4 == 0, "vnext_layernorm: C must be a positive multiple of 4 (got %d)", C);
     if (rows == 0) return VNEXT_OK;
     VNEXT_CHECK_ARG(x && gamma && beta && out, "vnext_layernorm: null pointer");
     long long blocks = (rows + 7) / 8;
     const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
-    layernorm_rows_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float4 *)x, (const float4 *)gamma,
-                                                                        (const float4 *)beta, (float4 *)out, rows, C / 4, eps);
+    const float4 *g = (const float4 *)gamma, *b = (const float4 *)beta;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (in_dtype == VNEXT_F32 && out_dtype == VNEXT_F32)
+        layernorm_rows_kernel<float, float><<<(int)blocks, 256, 0, st>>>((const float *)x, g, b, (float *)out, rows, C / 4, eps);
+    else if (in_dtype == VNEXT_F32)
+        layernorm_rows_kernel<float, __nv_bfloat16><<<(int)blocks, 256, 0, st>>>((const float *)x, g, b, (__nv_bfloat16 *)out, rows, C / 4, eps);
+    else if (out_dtype == VNEXT_F32)
+        layernorm_rows_kernel<__nv_bfloat16, float><<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16 *)x, g, b, (float *)out, rows, C / 4, eps);
+    else
+        layernorm_rows_kernel<__nv_bfloat16, __nv_bfloat16><<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16 *)x, g, b, (__nv_bfloat16 *)out, rows, C / 4, eps);
     count_launch();
     VNEXT_CUDA(cudaGetLastError());
     return VNEXT_OK;
+}
+
+int vnext_layernorm(const float *x, const float *gamma, const float *beta, float *out, long long rows, int C, float eps,
+                    void *stream) {
+    return vnext_layernorm_dt(VNEXT_F32, VNEXT_F32, x, gamma, beta, out, rows, C, eps, stream);
 }
 
 }  // extern "C"

@@ -24,8 +24,9 @@ constexpr int kTcNK = 160;                 // kTcMaxN rounded up to a multiple o
 constexpr int kTcTmemCols = 256;           // S/P: 160, O block 0: 32, O block 1: 32
 
 struct WinAttnTcParams {
-    const float *qkv, *qkv_bias, *table;
-    float *out;
+    const void *qkv;               // IOT [B, H, W, 3C]
+    const float *qkv_bias, *table;
+    void *out;                     // IOT [B, H, W, C]
     int B, H, W, Hp, Wp, C, heads, ws, shift, items;
     float scale;
 };
@@ -78,6 +79,9 @@ constexpr int kOffTok = kOffBias + 532 * 4;                // kTcMaxN ints
 constexpr int kOffReg = kOffTok + kTcMaxN * 4;
 constexpr int kTcSmemBytes = kOffReg + kTcMaxN * 4 + 1024;
 
+// IOT: storage type of qkv and out (fp32 or bf16); the MMAs are TF32 on fp32 shared-memory operands either way (the gather
+// widens bf16 on the fly: half the global bytes in, half out).
+template <typename IOT>
 __global__ void __launch_bounds__(kTcThreads, 2) swin_window_attention_tc_kernel(const WinAttnTcParams p) {
     extern __shared__ unsigned char tc_raw[];
     unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~(uintptr_t)1023);
@@ -138,10 +142,14 @@ __global__ void __launch_bounds__(kTcThreads, 2) swin_window_attention_tc_kernel
         for (int i = tid; i < N * 8; i += kTcThreads) {
             const int t = i >> 3, cq = i & 7, c4 = cq * 4;
             const int tok = stok[t];
-            const float *r = tok >= 0 ? p.qkv + (size_t)tok * 3 * p.C + h * 32 + c4 : p.qkv_bias + h * 32 + c4;
-            const float4 q = *reinterpret_cast<const float4 *>(r);
-            const float4 k = *reinterpret_cast<const float4 *>(r + p.C);
-            const float4 v = *reinterpret_cast<const float4 *>(r + 2 * p.C);
+            float4 q, k, v;
+            if (tok >= 0) {
+                const IOT *r = reinterpret_cast<const IOT *>(p.qkv) + (size_t)tok * 3 * p.C + h * 32 + c4;
+                q = load4(r); k = load4(r + p.C); v = load4(r + 2 * p.C);
+            } else {        // zero-padded token: q / k / v are the projection bias
+                const float *r = p.qkv_bias + h * 32 + c4;
+                q = load4(r); k = load4(r + p.C); v = load4(r + 2 * p.C);
+            }
             const int sw = (cq ^ (t & 7)) << 4;
             *reinterpret_cast<float4 *>(sm + kOffQ + t * 128 + sw) = make_float4(q.x * p.scale, q.y * p.scale, q.z * p.scale, q.w * p.scale);
             *reinterpret_cast<float4 *>(sm + kOffK + t * 128 + sw) = k;
@@ -236,16 +244,16 @@ __global__ void __launch_bounds__(kTcThreads, 2) swin_window_attention_tc_kernel
                 uint32_t v[16];
                 const float inv = 1.f / sum;
                 const int tok = i < N ? stok[i] : -1;
-                float *orow = p.out + (size_t)max(tok, 0) * p.C + h * 32;
+                IOT *orow = reinterpret_cast<IOT *>(p.out) + (size_t)max(tok, 0) * p.C + h * 32;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     tc_ld16(lane_addr + kTcNK + mb * 32 + half * 16, v);
                     if (tok >= 0) {
 #pragma unroll
                         for (int j = 0; j < 16; j += 4)
-                            *reinterpret_cast<float4 *>(orow + half * 16 + j) =
-                                make_float4(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv,
-                                            __uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
+                            store4(orow + half * 16 + j,
+                                   make_float4(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv,
+                                               __uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv));
                     }
                 }
             }
@@ -265,9 +273,9 @@ __global__ void __launch_bounds__(kTcThreads, 2) swin_window_attention_tc_kernel
 
 using namespace vnext;
 
-extern "C" int vnext_swin_window_attention_tc(const float *qkv, const float *qkv_bias, const float *rel_pos_bias_table,
-                                              float *out, int B, int H, int W, int C, int heads, int window, int shift,
-                                              void *stream) {
+static int swin_tc_launch(int io_dtype, const void *qkv, const float *qkv_bias, const float *rel_pos_bias_table, void *out, int B,
+                          int H, int W, int C, int heads, int window, int shift, void *stream) {
+    VNEXT_CHECK_ARG(io_dtype == VNEXT_F32 || io_dtype == VNEXT_BF16, "vnext_swin_window_attention_tc: dtype must be fp32 (0) or bf16 (2)");
     VNEXT_CHECK_ARG(B >= 0 && H > 0 && W > 0 && heads > 0 && C == heads * 32,
                     "vnext_swin_window_attention_tc: needs C == heads * 32 (got C=%d heads=%d)", C, heads);
     VNEXT_CHECK_ARG(window >= 4 && window <= 12 && shift >= 0 && shift < window,
@@ -287,12 +295,28 @@ extern "C" int vnext_swin_window_attention_tc(const float *qkv, const float *qkv
     p.items = (int)items;
     static bool configured = false;
     if (!configured) {
-        VNEXT_CUDA(cudaFuncSetAttribute(swin_window_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+        VNEXT_CUDA(cudaFuncSetAttribute(swin_window_attention_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+        VNEXT_CUDA(cudaFuncSetAttribute(swin_window_attention_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
         configured = true;
     }
     const int grid = (int)(items < 2ll * num_sms() ? items : 2ll * num_sms());
-    swin_window_attention_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, (cudaStream_t)stream>>>(p);
+    if (io_dtype == VNEXT_F32)
+        swin_window_attention_tc_kernel<float><<<grid, kTcThreads, kTcSmemBytes, (cudaStream_t)stream>>>(p);
+    else
+        swin_window_attention_tc_kernel<__nv_bfloat16><<<grid, kTcThreads, kTcSmemBytes, (cudaStream_t)stream>>>(p);
     count_launch();
     VNEXT_CUDA(cudaGetLastError());
     return VNEXT_OK;
+}
+
+extern "C" int vnext_swin_window_attention_tc(const float *qkv, const float *qkv_bias, const float *rel_pos_bias_table,
+                                              float *out, int B, int H, int W, int C, int heads, int window, int shift,
+                                              void *stream) {
+    return swin_tc_launch(VNEXT_F32, qkv, qkv_bias, rel_pos_bias_table, out, B, H, W, C, heads, window, shift, stream);
+}
+
+extern "C" int vnext_swin_window_attention_tc_dt(int io_dtype, const void *qkv, const float *qkv_bias,
+                                                 const float *rel_pos_bias_table, void *out, int B, int H, int W, int C,
+                                                 int heads, int window, int shift, void *stream) {
+    return swin_tc_launch(io_dtype, qkv, qkv_bias, rel_pos_bias_table, out, B, H, W, C, heads, window, shift, stream);
 }

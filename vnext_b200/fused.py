@@ -75,30 +75,39 @@ def preprocess(frames, mean, std, Hp, Wp, out=None, out_dtype=torch.float32):
     return out
 
 
-def layernorm(x, gamma, beta, eps=1e-5, out=None):
-    """Row LayerNorm over the last dimension (contiguous rows)."""
+def layernorm(x, gamma, beta, eps=1e-5, out=None, out_dtype=None):
+    """Row LayerNorm over the last dimension (contiguous rows); x / out fp32 or bf16, statistics fp32."""
     C = x.shape[-1]
     assert x.is_contiguous()
-    out = torch.empty_like(x) if out is None else out
+    out = torch.empty(x.shape, dtype=out_dtype or x.dtype, device=x.device) if out is None else out
     rows = x.numel() // C
-    rc = _cabi.timed_call("layernorm", {"bytes": 8.0 * x.numel()}, x, lambda: _cabi.lib().vnext_layernorm(
-        x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), rows, C, float(eps), _st(x)))
+    info = {"bytes": float(x.element_size() * x.numel() + out.element_size() * x.numel())}
+    rc = _cabi.timed_call("layernorm", info, x, lambda: _cabi.lib().vnext_layernorm_dt(
+        _DT[x.dtype], _DT[out.dtype], x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), rows, C, float(eps), _st(x)))
     _cabi.check(rc, "vnext_layernorm")
     return out
 
 
 def swin_window_attention(qkv, qkv_bias, table, heads, window, shift, tensor_cores=False):
-    """qkv [B,H,W,3C] contiguous -> attention output [B,H,W,C] (input of the block's proj Linear).
-    tensor_cores: tcgen05 TF32 kernel (csrc/swin_attention_tc.cu) instead of the exact-fp32 SIMT kernel."""
+    """qkv [B,H,W,3C] contiguous -> attention output [B,H,W,C] (input of the block's proj Linear), same dtype as qkv.
+    tensor_cores: tcgen05 TF32 kernel (csrc/swin_attention_tc.cu; fp32 or bf16 storage) instead of the exact-fp32 SIMT kernel."""
     B, H, W, C3 = qkv.shape
     C = C3 // 3
     assert qkv.is_contiguous() and table.is_contiguous()
     out = torch.empty((B, H, W, C), dtype=qkv.dtype, device=qkv.device)
     n = window * window
-    info = {"bytes": 4.0 * (qkv.numel() + out.numel()), "flops": 4.0 * B * (-(-H // window)) * (-(-W // window)) * heads * n * n * 32}
-    fn = _cabi.lib().vnext_swin_window_attention_tc if (tensor_cores and window >= 4) else _cabi.lib().vnext_swin_window_attention
-    rc = _cabi.timed_call("swin_window_attention_tc" if (tensor_cores and window >= 4) else "swin_window_attention", info, qkv, lambda: fn(
-        qkv.data_ptr(), qkv_bias.data_ptr(), table.data_ptr(), out.data_ptr(), B, H, W, C, heads, window, shift, _st(qkv)))
+    e = qkv.element_size()
+    info = {"bytes": float(e) * (qkv.numel() + out.numel()), "flops": 4.0 * B * (-(-H // window)) * (-(-W // window)) * heads * n * n * 32}
+    tc = tensor_cores and window >= 4
+    if not tc and qkv.dtype != torch.float32:
+        raise RuntimeError("swin_window_attention: bf16 storage needs the tensor-core kernel (window >= 4)")
+    if tc:
+        call = lambda: _cabi.lib().vnext_swin_window_attention_tc_dt(
+            _DT[qkv.dtype], qkv.data_ptr(), qkv_bias.data_ptr(), table.data_ptr(), out.data_ptr(), B, H, W, C, heads, window, shift, _st(qkv))
+    else:
+        call = lambda: _cabi.lib().vnext_swin_window_attention(
+            qkv.data_ptr(), qkv_bias.data_ptr(), table.data_ptr(), out.data_ptr(), B, H, W, C, heads, window, shift, _st(qkv))
+    rc = _cabi.timed_call("swin_window_attention_tc" if tc else "swin_window_attention", info, qkv, call)
     _cabi.check(rc, "vnext_swin_window_attention")
     return out
 

@@ -107,8 +107,6 @@ class SeqFormerEngine:
         self._small_fp32 = os.environ.get("VNEXT_SMALL_FP32", "0") == "1"
         parts = os.environ.get("VNEXT_BF16_PARTS", "backbone,encoder").split(",")     # experiment switch (tools/bf16_error_budget.py)
         self.bb_dtype = self.act_dtype if "backbone" in parts else torch.float32      # backbone + input projection storage
-        if swin is not None:
-            self.bb_dtype = torch.float32      # the Swin kernels (window attention, row LayerNorm) are fp32 / TF32 only
         self.val_dtype = self.act_dtype if ("encoder" in parts or "value" in parts) else torch.float32    # MSDA value / sampled
         self.hid_dtype = self.act_dtype if ("encoder" in parts or "hidden" in parts) else torch.float32   # FFN hidden
         self._plans: Dict[Tuple[int, int, int], ClipPlan] = {}

@@ -40,10 +40,10 @@ class SwinBackbone:
             self.stages.append(st)
 
     # ------------------------------------------------------------------ pieces
-    def _ln(self, x, wb):
+    def _ln(self, x, wb, out_dtype=None):
         if self.eng.native:
             from .. import fused
-            return fused.layernorm(x.contiguous(), wb[0], wb[1])
+            return fused.layernorm(x.contiguous(), wb[0], wb[1], out_dtype=out_dtype)
         return F.layer_norm(x, (x.shape[-1],), wb[0], wb[1], 1e-5)
 
     def _attention(self, qkv, blk):
@@ -58,23 +58,30 @@ class SwinBackbone:
         """x: [T, 3, H, W] normalised frames (H, W multiples of 32) -> {"res2".."res5": [T, h, w, C] channels-last}."""
         T, _, H, W = x.shape
         ps, lin = self.ps, self.eng.lin
+        # bf16 mode (engine precision "bf16" on the CUDA kernels): the residual stream `tok` stays fp32; LayerNorm hands bf16
+        # rows to the bf16 GEMMs (qkv, proj, fc1, fc2, patch merging), qkv and the attention output are bf16 (the attention
+        # kernel's MMAs are TF32 on operands widened in its gather), the GELU hidden is bf16
+        act = getattr(self.eng, "bb_dtype", torch.float32) if self.eng.native else torch.float32
+        mixed = act == torch.bfloat16
+        f32 = {"out_dtype": torch.float32} if mixed else {}
         xh = x.permute(0, 2, 3, 1)
         h, w = H // ps, W // ps
         patches = xh.reshape(T, h, ps, w, ps, 3).permute(0, 1, 3, 2, 4, 5).reshape(T, h, w, ps * ps * 3)
-        tok = self._ln(lin(patches, self.patch), self.patch_norm)
+        tok = self._ln(lin(patches, self.patch), self.patch_norm, **f32)
         feats = {}
         for i, st in enumerate(self.stages):
             for blk in st["blocks"]:
-                att = self._attention(lin(self._ln(tok, blk["norm1"]), blk["qkv"]), blk)
-                tok = lin(att, blk["proj"], residual=tok)
-                tok = lin(lin(self._ln(tok, blk["norm2"]), blk["fc1"], gelu=True), blk["fc2"], residual=tok)
-            feats[f"res{i + 2}"] = self._ln(tok, st["norm"])
+                att = self._attention(lin(self._ln(tok, blk["norm1"], act if mixed else None), blk["qkv"]), blk)
+                tok = lin(att, blk["proj"], residual=tok, **f32)
+                tok = lin(lin(self._ln(tok, blk["norm2"], act if mixed else None), blk["fc1"], gelu=True), blk["fc2"],
+                          residual=tok, **f32)
+            feats[f"res{i + 2}"] = self._ln(tok, st["norm"], act if mixed else None)
             if st["merge"] is not None:
                 if h % 2 or w % 2:
                     tok = F.pad(tok, (0, 0, 0, w % 2, 0, h % 2))
                 tok = torch.cat([tok[:, 0::2, 0::2], tok[:, 1::2, 0::2], tok[:, 0::2, 1::2], tok[:, 1::2, 1::2]], -1)
                 h, w = (h + 1) // 2, (w + 1) // 2
-                tok = lin(self._ln(tok, st["merge"][0]), st["merge"][1])
+                tok = lin(self._ln(tok, st["merge"][0], act if mixed else None), st["merge"][1], **f32)
         return feats
 
 
