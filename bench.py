@@ -138,8 +138,9 @@ def cpu_oracle_fps(T, H, W, steps, warmup, budget_s=240.0):
             SO.whole_video_postprocess(SO.inference(sd, frames), (H, W))
         dt = time.perf_counter() - t0
     fps = n_steps * T / dt
-    desc = (f"oracle port (oracle/seqformer_oracle.py, torch {torch.__version__} CPU, {cores} of {os.cpu_count()} host threads, "
-            f"fastest of 16/32/64/all): {n_steps} timed step(s) of the full {T}-frame clip at {H}x{W} "
+    from vnext_b200.hostcfg import cpu_quota
+    desc = (f"oracle port (oracle/seqformer_oracle.py, torch {torch.__version__} CPU, {cores} threads — fastest of 16/32/64/all; "
+            f"{os.cpu_count()} visible CPUs, cgroup quota {cpu_quota()}): {n_steps} timed step(s) of the full {T}-frame clip at {H}x{W} "
             f"({dt / n_steps:.2f} s/step; {n_warm} warm-up clip)")
     return fps, desc, cores, dt / n_steps * 1e3, n_steps
 
@@ -334,10 +335,11 @@ def own_arm(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        # one process per GPU on ONE host: without a cap every rank spins up cpu_count intra-op threads for its host-side
-        # staging copies and the ranks oversubscribe each other (end-to-end efficiency 0.76 at 8 GPUs in round 1)
-        torch.set_num_threads(max(1, min(16, (os.cpu_count() or world) // world)))
+    # torch sizes its intra-op pool from the VISIBLE CPUs (128 on these boxes) while the container's CFS quota is 16: the
+    # staging copies then get the cgroup throttled and every ~6th clip stalls for 21 ms (vnext_b200/hostcfg.py; this was
+    # the end-to-end efficiency of 0.76 at 8 GPUs and the box-to-box variance of round 1's e2e numbers)
+    from vnext_b200.hostcfg import cpu_quota, tune_host_threads
+    host_threads = tune_host_threads(ranks_on_host=world)
     T, H, W = WORKLOADS[args.workload]
     swin = None
     if args.workload.startswith("swinl"):           # BASELINE config 4's backbone (tf32 here; bf16 is a later round)
@@ -565,7 +567,8 @@ def own_arm(args, rank, world, local_rank):
                 "d2h_bytes_per_step": run.d2h_bytes, "instances_returned": len(res["pred_scores"]),
                 "api": "SeqFormer.forward(batched_inputs), one synchronous call per clip",
                 "pipelined_value": round(e2e_stream_fps, 2),
-                "pipelined_api": "SeqFormer.stream(iterable): same inputs/outputs, 2 clips in flight"},
+                "pipelined_api": "SeqFormer.stream(iterable): same inputs/outputs, 2 clips in flight",
+                "host_threads": host_threads, "host_cpu_quota": cpu_quota()},
         "gpu_launches": int(launches_per_step * args.steps),
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "also": also, "also_bf16": also_bf16,
         "stock_cuda_op": stock, "gpu_eager_baseline": eager,

@@ -16,6 +16,9 @@ from vnext_b200.seqformer.meta_arch import SeqFormer  # noqa: E402
 def main():
     T, H, W = 5, 720, 1280
     precision = sys.argv[1] if len(sys.argv) > 1 else "tf32"
+    if os.environ.get("VNEXT_TUNE_THREADS", "1") == "1":
+        from vnext_b200.hostcfg import tune_host_threads
+        tune_host_threads()
     model = SeqFormer(device="cuda", precision=precision)
     model.load_reference_state_dict(bench.make_weights(0))
     model.eval()

@@ -9,8 +9,25 @@ Host<->device traffic per clip: the uint8 frames in (pinned), the top-k scores a
 import torch
 
 
+_warned_threads = False
+
+
+def _warn_if_oversubscribed():
+    global _warned_threads
+    if _warned_threads:
+        return
+    _warned_threads = True
+    from ..hostcfg import cpu_quota
+    if torch.get_num_threads() > 2 * cpu_quota():
+        import warnings
+        warnings.warn(f"vnext_b200: torch uses {torch.get_num_threads()} intra-op threads but this process may use "
+                      f"{cpu_quota()} CPUs (cgroup quota): the host staging copies will be throttled and clips will stall; call "
+                      "vnext_b200.hostcfg.tune_host_threads() once at start-up")
+
+
 class ClipRunner:
     def __init__(self, engine, T, H, W, ori_size=None, topk=10, use_graph=True):
+        _warn_if_oversubscribed()
         self.engine, self.T, self.H, self.W = engine, T, H, W
         self.ori_size = tuple(ori_size) if ori_size is not None else (H, W)
         self.topk = topk
