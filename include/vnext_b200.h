@@ -197,6 +197,17 @@ int vnext_conv3x3_strided_tc(int in_dtype, int out_dtype, const void *x, const v
                              void *out, int T, int H, int W, int Cin, int Cout, int stride, int relu, void *stream);
 
 /*
+ * ResNet stem on the tensor cores: normalise + zero-pad the frames (as vnext_preprocess) and convolve 7x7 / stride 2 / padding 3
+ * (3 -> Cout channels; BasicStem.conv1, detectron2/modeling/backbone/resnet.py:355-359) as an implicit GEMM — no im2col buffer:
+ * the frames are written once as a zero-bordered 4-channel image into `scratch` ([T, Hp+6, Wp+6, 4] fp32) and each filter row is
+ * one TMA box of an overlapping tensor-map view of it.  weight_packed [Cout, 7, 8, 4] fp32 = the conv weight as (ky, kx, c) with
+ * kx padded 7 -> 8 and c padded 3 -> 4 by zeros.  out [T, Hp/2, Wp/2, Cout] (fp32 or bf16) = conv (+ bias, ReLU if asked).
+ */
+int vnext_stem_conv7x7(int in_is_u8, int out_dtype, const void *frames, const float *weight_packed, const float *bias, void *out,
+                       float *scratch, int T, int H, int W, int Hp, int Wp, int Cout, const float *mean3, const float *std3, int relu,
+                       void *stream);
+
+/*
  * Multi-head self-attention over a few hundred queries (the decoder's object queries), head_dim 32:
  *   out[b, i, h*32 + c] = sum_j softmax_j(q_i . k_j / sqrt(32)) v_j[c]   per (batch b, head h)
  * with q | k | v read in place from the merged in-projection qkv [batch, n, >= 3*heads*32] (row pitch ld floats: q at

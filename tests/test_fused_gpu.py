@@ -85,3 +85,26 @@ def test_mask_finalize_kernel(H, W, OH, OW):
     want = F.interpolate(pm, size=(OH, OW), mode="nearest") > 0.5
     assert got.dtype == torch.bool and got.shape == want.shape
     assert (got == want).float().mean().item() > 0.9995
+
+
+@pytest.mark.parametrize("T,H,W,u8", [(2, 96, 128, True), (1, 70, 100, False), (5, 480, 864, True), (1, 33, 260, True)])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_stem_conv7x7_on_tensor_cores(T, H, W, u8, out_dtype):
+    """Normalise + pad + 7x7/s2/p3 stem as one implicit GEMM (overlapping TMA view of a zero-bordered 4-channel image) vs
+    F.conv2d of the reference preprocessing (S/seqformer.py:413-429 + S/util/misc.py:288-316; resnet.py:355-359)."""
+    import torch.nn.functional as F
+    from vnext_b200 import fused
+    g = torch.Generator().manual_seed(T * 7 + H)
+    fr = torch.randint(0, 256, (T, 3, H, W), generator=g)
+    fr = fr.to(torch.uint8) if u8 else fr.float() + 0.25
+    w = (torch.randn(64, 3, 7, 7, generator=g) / 12).cuda()
+    mean, std = (123.675, 116.28, 103.53), (58.395, 57.12, 57.375)
+    Hp, Wp = (H + 31) // 32 * 32, (W + 31) // 32 * 32
+    x = (fr.double().cuda() - torch.tensor(mean, dtype=torch.double, device="cuda").view(1, 3, 1, 1)) / \
+        torch.tensor(std, dtype=torch.double, device="cuda").view(1, 3, 1, 1)
+    x = F.pad(x, (0, Wp - W, 0, Hp - H))
+    want = F.conv2d(x, w.double(), None, stride=2, padding=3).permute(0, 2, 3, 1)
+    got = fused.stem_conv7x7(fr.cuda(), fused.pack_stem_weight(w), mean, std, Hp, Wp, out_dtype=out_dtype)
+    assert got.shape == want.shape and got.dtype == out_dtype
+    tol = (2e-3 if out_dtype == torch.float32 else 8e-3) * want.abs().max().item()
+    assert (got.double() - want).abs().max().item() < tol

@@ -187,6 +187,30 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const T *__restrict__ i
     }
 }
 
+// Same normalisation, written for the tensor-core stem (gemm_tcgen05.cu: stem_conv_device): [T, Hp + 6, Wp + 6, 4] fp32 with a
+// 3-pixel zero border (the convolution's padding; the /32 padding of the frame is zero too) and a zero 4th channel.
+template <typename T>
+__global__ void __launch_bounds__(256) preprocess_padded4_kernel(const T *__restrict__ in, float4 *__restrict__ out, int Tn, int H,
+                                                                 int W, int Hp, int Wp, float m0, float m1, float m2, float s0,
+                                                                 float s1, float s2) {
+    const int Wq = Wp + 6, Hq = Hp + 6;
+    const long long total = (long long)Tn * Hq * Wq;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int xq = (int)(i % Wq);
+        const long long t2 = i / Wq;
+        const int yq = (int)(t2 % Hq), t = (int)(t2 / Hq);
+        const int h = yq - 3, w = xq - 3;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (h >= 0 && h < H && w >= 0 && w < W) {
+            const long long base = ((long long)t * 3 * H + h) * W + w;
+            v.x = ((float)in[base] - m0) / s0;
+            v.y = ((float)in[base + (long long)H * W] - m1) / s1;
+            v.z = ((float)in[base + 2ll * H * W] - m2) / s2;
+        }
+        out[i] = v;
+    }
+}
+
 static inline int grid_for(long long work_items, int threads) {
     long long b = (work_items + threads - 1) / threads;
     const long long cap = (long long)num_sms() * 8;
@@ -194,6 +218,11 @@ static inline int grid_for(long long work_items, int threads) {
 }
 
 }  // namespace vnext
+
+namespace vnext {   // defined in gemm_tcgen05.cu
+int stem_conv_device(int out_dt, const float *xpad, const float *w, const float *bias, void *out, int T, int Hp, int Wp, int Cout,
+                     int relu, cudaStream_t stream);
+}
 
 using namespace vnext;
 
@@ -318,6 +347,31 @@ int vnext_preprocess_dt(int in_is_u8, int out_dtype, const void *frames, void *o
     VNEXT_CUDA(cudaGetLastError());
     return VNEXT_OK;
 }
+int vnext_stem_conv7x7(int in_is_u8, int out_dtype, const void *frames, const float *weight_packed, const float *bias, void *out,
+                       float *scratch, int T, int H, int W, int Hp, int Wp, int Cout, const float *mean3, const float *std3, int relu,
+                       void *stream) {
+    VNEXT_CHECK_ARG(dt_ok(out_dtype), "vnext_stem_conv7x7: out dtype must be fp32 or bf16");
+    VNEXT_CHECK_ARG(T >= 0 && H > 0 && W > 0 && Hp >= H && Wp >= W && Hp % 2 == 0 && Wp % 2 == 0 && Cout > 0 && Cout % 8 == 0,
+                    "vnext_stem_conv7x7: bad shape (H %d W %d Hp %d Wp %d Cout %d)", H, W, Hp, Wp, Cout);
+    if (T == 0) return VNEXT_OK;
+    VNEXT_CHECK_ARG(frames && weight_packed && out && scratch && mean3 && std3 &&
+                        (reinterpret_cast<uintptr_t>(scratch) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(weight_packed) & 15) == 0,
+                    "vnext_stem_conv7x7: null or unaligned pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)T * (Hp + 6) * (Wp + 6);
+    const int g = grid_for(total, 256);
+    if (in_is_u8)
+        preprocess_padded4_kernel<unsigned char><<<g, 256, 0, st>>>((const unsigned char *)frames, (float4 *)scratch, T, H, W, Hp, Wp,
+                                                                   mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]);
+    else
+        preprocess_padded4_kernel<float><<<g, 256, 0, st>>>((const float *)frames, (float4 *)scratch, T, H, W, Hp, Wp, mean3[0],
+                                                           mean3[1], mean3[2], std3[0], std3[1], std3[2]);
+    count_launch();
+    VNEXT_CUDA(cudaGetLastError());
+    return stem_conv_device(out_dtype, scratch, weight_packed, bias, out, T, Hp, Wp, Cout, relu, st);
+}
+
 int vnext_preprocess(int in_is_u8, const void *frames, float *out, int T, int H, int W, int Hp, int Wp, const float *mean3,
                      const float *std3, void *stream) {
     return vnext_preprocess_dt(in_is_u8, VNEXT_F32, frames, out, T, H, W, Hp, Wp, mean3, std3, stream);

@@ -167,6 +167,7 @@ struct GemmParams {
     const float *bias;       // [N] or null
     const float *bias2d;     // [period, ldb2] or null: added as bias2d[row % period][col] (geometry-dependent bias)
     int period, ldb2;
+    int pdl;                 // launched with programmatic stream serialization (see the kernel prologue)
     int b2_tma;              // the 2-D bias tile comes through shared memory (four 8-row TMA boxes, rows taken mod period)
     const unsigned char *row_mask;   // [period] or null: rows with mask != 0 get columns [0, mask_cols) zeroed
     int mask_cols;
@@ -244,7 +245,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     unsigned char *const epi_smem = smem + STAGES * STAGE_BYTES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_k_blocks = p.conv ? 9 * p.conv_cin_blocks : (p.K + BLOCK_K - 1) / BLOCK_K;
+    const int num_k_blocks = p.conv == 2 ? 7 : (p.conv ? 9 * p.conv_cin_blocks : (p.K + BLOCK_K - 1) / BLOCK_K);
     // work distribution: a work item is one output tile (cluster 1) or a vertical pair of tiles (cluster 2)
     const int csize = p.cluster;
     const uint32_t crank = csize > 1 ? cluster_ctarank() : 0u;
@@ -280,6 +281,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (csize > 1) cluster_sync_all();          // peers' barriers are initialised before anything remote touches them
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    if (p.pdl) {
+        // programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map prefetch) ran while the
+        // previous kernel of the stream was still finishing; its results are needed from here on.  Our own dependents may
+        // start their prologue right away — they wait for this grid's completion at the same point.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
 
     if (warp == 0 && lane == 0) {
         // ===================== TMA producer =====================
@@ -296,7 +304,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 unsigned char *sa = smem + stage * STAGE_BYTES, *sb = sa + A_BYTES;
                 mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-                if (p.conv) {
+                if (p.conv == 2) {
+                    // 7x7 stride-2 stem on a zero-bordered 4-channel image: k-block = filter row ky; the A tile is 128
+                    // consecutive output pixels x (8 input pixels x 4 channels = 32 floats, the 8th pixel meets zero weights);
+                    // neighbouring output pixels start 2 input pixels = 32 B apart: an OVERLAPPING tensor-map view (see
+                    // stem_conv_device) delivers the im2col rows without an im2col buffer
+                    const int mt = tile / p.num_n_tiles;
+                    const int tx = mt % p.conv_tiles_x, ty = (mt / p.conv_tiles_x) % p.conv_tiles_y;
+                    tma_load_4d(sa, &tmap_a, 0, tx * 128, 2 * ty + kb, mt / (p.conv_tiles_x * p.conv_tiles_y), &full_bar[stage]);
+                } else if (p.conv) {
                     const int mt = tile / p.num_n_tiles;
                     const int tx = mt % p.conv_tiles_x, ty = (mt / p.conv_tiles_x) % p.conv_tiles_y;
                     const int fr = mt / (p.conv_tiles_x * p.conv_tiles_y);
@@ -510,7 +526,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         fence_proxy_async();
                         __syncwarp();
                         if (lane == 0) {
-                            if (p.conv) {     // this warp's 32 tile rows = 2 image rows x 16 pixels of the 8 x 16 patch
+                            if (p.conv == 2) {   // this warp's 32 tile rows = 32 consecutive pixels of one output row
+                                const int mt = tile / p.num_n_tiles;
+                                const int tx = mt % p.conv_tiles_x, ty = (mt / p.conv_tiles_x) % p.conv_tiles_y;
+                                tma_store_4d(&tmap_out, ob, col0, tx * 128 + ew * 32, ty, mt / (p.conv_tiles_x * p.conv_tiles_y));
+                            } else if (p.conv) {     // this warp's 32 tile rows = 2 image rows x 16 pixels of the 8 x 16 patch
                                 const int mt = tile / p.num_n_tiles;
                                 const int tx = mt % p.conv_tiles_x, ty = (mt / p.conv_tiles_x) % p.conv_tiles_y;
                                 tma_store_4d(&tmap_out, ob, col0, tx * 16, ty * 8 + 2 * ew, mt / (p.conv_tiles_x * p.conv_tiles_y));
@@ -661,6 +681,23 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUten
         count_launch();
         return VNEXT_OK;
     }
+    static const bool want_pdl = getenv("VNEXT_GEMM_PDL") ? atoi(getenv("VNEXT_GEMM_PDL")) != 0 : false;
+    if (want_pdl) {
+        p.pdl = 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kGemmThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        VNEXT_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tr, p));
+        count_launch();
+        return VNEXT_OK;
+    }
     kern<<<grid, kGemmThreads, smem, stream>>>(ta, tb, to, tr, p);
     count_launch();
     VNEXT_CUDA(cudaGetLastError());
@@ -709,6 +746,7 @@ int linear_tc_device(const LinearArgs &x, cudaStream_t stream) {
     p.conv = p.conv_cin_blocks = p.conv_tiles_x = p.conv_tiles_y = 0;
     p.conv_stride = 1;
     p.cluster = 1;
+    p.pdl = 0;
     p.b2_tma = 0;
     p.vec_ok = al16(x.out) && x.ldo % oe == 0 && (!x.bias || al16(x.bias)) &&
                (!x.bias2d || (al16(x.bias2d) && x.ldb2 % 4 == 0)) && (!x.residual || (al16(x.residual) && x.ldr % oe == 0));
@@ -766,6 +804,7 @@ int conv3x3_tc_device(int in_dt, int out_dt, const void *x, const void *w, const
     p.conv_stride = stride;
     p.M = T * H * W; p.N = Cout; p.K = 9 * Cin; p.bias = bias; p.bias2d = nullptr; p.period = 1; p.ldb2 = 0;
     p.b2_tma = 0;
+    p.pdl = 0;
     p.row_mask = nullptr; p.mask_cols = 0; p.residual = nullptr; p.gamma = p.beta = nullptr; p.out = static_cast<float *>(out);
     p.ldo = Cout; p.ldr = 0; p.flags = relu ? EPI_RELU : 0; p.eps = 0.f; p.vec_ok = 1; p.tma_epi = 1;
     p.conv = 1; p.conv_cin_blocks = Cin / kbox; p.conv_tiles_x = (W + 15) / 16; p.conv_tiles_y = (H + 7) / 8;
@@ -786,6 +825,51 @@ int conv3x3_tc_device(int in_dt, int out_dt, const void *x, const void *w, const
     rc = make_tmap_nhwc(&to, out_dt, out, T, H, W, Cout, 2, 16, 32);
     if (rc) return rc;
     return launch_any(wide, in_dt, out_dt, ta, tb, to, to, p, stream);
+}
+
+// 7x7 stride-2 padding-3 convolution of a 3-channel image (the ResNet stem, detectron2/modeling/backbone/resnet.py:355-359) as
+// an implicit GEMM with K = 7 filter rows x 32.  `xpad`: [T, Hp + 6, Wp + 6, 4] fp32 — the normalised frame with a zero border
+// of 3 pixels and a zero 4th channel (written by vnext_stem_conv7x7's preprocess pass), so a pixel is 16 B and a filter row's
+// window of output pixel ox is the 32 floats starting at padded column 2*ox: tensor map dims {32, Wo, Hp + 6, T} with strides
+// {32 B, row pitch, image pitch} — rows overlap, every address is inside the buffer, no out-of-bounds fill needed.
+// `w`: [Cout, 7 * 32] (ky, kx padded to 8, channel padded to 4).
+int stem_conv_device(int out_dt, const float *xpad, const float *w, const float *bias, void *out, int T, int Hp, int Wp, int Cout,
+                     int relu, cudaStream_t stream) {
+    const int Ho = Hp / 2, Wo = Wp / 2;
+    GemmParams p;
+    p.M = T * Ho * Wo; p.N = Cout; p.K = 7 * 32; p.bias = bias; p.bias2d = nullptr; p.period = 1; p.ldb2 = 0;
+    p.b2_tma = 0; p.pdl = 0;
+    p.row_mask = nullptr; p.mask_cols = 0; p.residual = nullptr; p.gamma = p.beta = nullptr; p.out = static_cast<float *>(out);
+    p.ldo = Cout; p.ldr = 0; p.flags = relu ? EPI_RELU : 0; p.eps = 0.f; p.vec_ok = 1; p.tma_epi = 1;
+    p.conv = 2; p.conv_cin_blocks = 1; p.conv_stride = 2; p.conv_tiles_x = (Wo + 127) / 128; p.conv_tiles_y = Ho;
+    p.num_m_tiles = T * p.conv_tiles_x * p.conv_tiles_y;
+    p.num_n_tiles = 0;
+    p.cluster = 1;
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return VNEXT_ECUDA;
+    }
+    CUtensorMap ta, tb, to;
+    {
+        const cuuint64_t rowpitch = (cuuint64_t)(Wp + 6) * 16, imgpitch = rowpitch * (Hp + 6);
+        cuuint64_t dims[4] = {32, (cuuint64_t)Wo, (cuuint64_t)(Hp + 6), (cuuint64_t)T};
+        cuuint64_t strides[3] = {32, rowpitch, imgpitch};
+        cuuint32_t box[4] = {32u, 128u, 1u, 1u};
+        cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+        CUresult r = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(xpad), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled (stem im2col view) failed (%d)", (int)r);
+            return VNEXT_ECUDA;
+        }
+    }
+    int rc = make_tmap_2d(&tb, VNEXT_F32, w, Cout, 7 * 32, 7 * 32, 128, 32);
+    if (rc) return rc;
+    rc = make_tmap_nhwc(&to, out_dt, out, T, Ho, Wo, Cout, 1, 32, 32);
+    if (rc) return rc;
+    return launch_any(false, VNEXT_F32, out_dt, ta, tb, to, to, p, stream);
 }
 
 }  // namespace vnext

@@ -243,11 +243,12 @@ __global__ void __launch_bounds__(kCachedThreads, 1) msda_fwd_cached_kernel(cons
                     float mx = cur.live ? a : -INFINITY;
 #pragma unroll
                     for (int o = LK / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                    const float e = cur.live ? expf(a - mx) : 0.f;
+                    // fast exp / divide (2 ulp): the softmax weights enter a 1e-4-tolerance sum, not an index
+                    const float e = cur.live ? __expf(a - mx) : 0.f;
                     float sum = e;
 #pragma unroll
                     for (int o = LK / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                    a = cur.live ? e / sum : 0.f;
+                    a = cur.live ? __fdividef(e, sum) : 0.f;
                 } else {
                     x = in.a0;
                     y = in.a1;

@@ -75,6 +75,39 @@ def preprocess(frames, mean, std, Hp, Wp, out=None, out_dtype=torch.float32):
     return out
 
 
+def stem_conv7x7(frames, weight_packed, mean, std, Hp, Wp, out_dtype=torch.float32, bias=None, relu=False):
+    """frames [T,3,H,W] uint8 / float32 (0..255) on the device -> conv7x7/s2/p3 of the normalised, zero-padded frames:
+    [T, Hp/2, Wp/2, Cout] channels-last (tensor-core implicit GEMM, csrc/gemm_tcgen05.cu stem_conv_device).
+    weight_packed [Cout, 7*8*4] fp32 (see pack_stem_weight)."""
+    T, _, H, W = frames.shape
+    Cout = weight_packed.shape[0]
+    assert frames.is_contiguous() and frames.dtype in (torch.uint8, torch.float32) and weight_packed.is_contiguous()
+    out = torch.empty((T, Hp // 2, Wp // 2, Cout), dtype=out_dtype, device=frames.device)
+    scratch = torch.empty((T, Hp + 6, Wp + 6, 4), dtype=torch.float32, device=frames.device)
+    m = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    sd = (ctypes.c_float * 3)(*[float(v) for v in std])
+    info = {"bytes": float(frames.numel() * frames.element_size() + 2 * scratch.numel() * 4 + out.numel() * out.element_size()),
+            "flops": 2.0 * out.numel() * 147}
+    rc = _cabi.timed_call("stem_conv7x7", info, frames, lambda: _cabi.lib().vnext_stem_conv7x7(
+        int(frames.dtype == torch.uint8), _DT[out.dtype], frames.data_ptr(), weight_packed.data_ptr(), _ptr_or_none(bias),
+        out.data_ptr(), scratch.data_ptr(), T, H, W, Hp, Wp, Cout, ctypes.cast(m, ctypes.c_void_p), ctypes.cast(sd, ctypes.c_void_p),
+        int(relu), _st(frames)))
+    _cabi.check(rc, "vnext_stem_conv7x7")
+    return out
+
+
+def pack_stem_weight(w):
+    """[Cout, 3, 7, 7] conv weight -> [Cout, 7 * 8 * 4] (ky, kx padded 7 -> 8, channel padded 3 -> 4 with zeros), fp32."""
+    Cout = w.shape[0]
+    p = torch.zeros((Cout, 7, 8, 4), dtype=torch.float32, device=w.device)
+    p[:, :, :7, :3] = w.float().permute(0, 2, 3, 1)
+    return p.reshape(Cout, 7 * 8 * 4).contiguous()
+
+
+def _ptr_or_none(t):
+    return None if t is None else t.data_ptr()
+
+
 def layernorm(x, gamma, beta, eps=1e-5, out=None, out_dtype=None):
     """Row LayerNorm over the last dimension (contiguous rows); x / out fp32 or bf16, statistics fp32."""
     C = x.shape[-1]

@@ -32,7 +32,7 @@ def cpu_quota():
     return n
 
 
-def tune_host_threads(ranks_on_host=1, cap=8):
+def tune_host_threads(ranks_on_host=1, cap=4):
     """Cap torch's intra-op pool at min(cap, quota / ranks_on_host) — the GPU path needs a few host threads for staging
     copies, never dozens.  Returns the thread count in effect."""
     import torch

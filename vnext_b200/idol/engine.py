@@ -41,16 +41,25 @@ class IDOLEngine(SeqFormerEngine):
         prev_ref = ref
         for lid, w in enumerate(self.dec):
             ref_in = ref[:, :, None] * (torch.cat([vr, vr], -1) if ref.shape[-1] == 4 else vr)[:, None]
-            q = out + qpos
-            out = self._mha(q, out, w["self_attn"], residual=out, ln=w["norm2"])
             a = w["attn"]
-            oa = self.lin(out + qpos, (a["oa_w"], a["oa_b"]))
+            if self.native_gemm and out.dtype == torch.float32:
+                # merged q | k | v projection with the query-position term as a 2-D bias + one attention kernel (see
+                # SeqFormerEngine._mha_self); same for the offsets | logits projection
+                out = self._mha_self(out.contiguous(), w["self_attn"], (lid, "sa"), w["norm2"])
+                oa = self.lin(out, (a["oa_w"], None), bias2d=self._qpos_bias((lid, "oa"), a["oa_w"], a["oa_b"]))
+            else:
+                q = out + qpos
+                out = self._mha(q, out, w["self_attn"], residual=out, ln=w["norm2"])
+                oa = self.lin(out + qpos, (a["oa_w"], a["oa_b"]))
             s = self.sample(self._value(memory, a, plan), oa, ref_in, plan, a["n_off"]).float()
             out = self.lin(s, (a["o_w"], a["o_b"]), residual=out, ln=w["norm1"])
             out = self.lin(self.lin(out, w["linear1"], relu=True), w["linear2"], residual=out, ln=w["norm3"])
             tmp = self._mlp(out, w["bbox"])
             prev_ref = ref
-            if ref.shape[-1] == 4:
+            if self.native_gemm and tmp.dtype == torch.float32:
+                from .. import fused
+                ref = fused.box_refine(tmp, ref)
+            elif ref.shape[-1] == 4:
                 ref = (tmp + inverse_sigmoid(ref)).sigmoid()
             else:
                 ref = torch.cat([tmp[..., :2] + inverse_sigmoid(ref), tmp[..., 2:]], -1).sigmoid()

@@ -54,6 +54,14 @@ class ClipPlan:
     extra: Dict = field(default_factory=dict)
 
 
+class RawFrames:
+    """Un-normalised frames handed from preprocess() to the native ResNet stem, which normalises, pads and convolves them
+    in one C-ABI call (vnext_stem_conv7x7)."""
+
+    def __init__(self, frames, plan):
+        self.frames, self.plan = frames, plan
+
+
 def inverse_sigmoid(x, eps=1e-5):
     x = x.clamp(min=0, max=1)
     return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
@@ -361,6 +369,8 @@ class SeqFormerEngine:
     # ------------------------------------------------------------------ stages
     def preprocess(self, frames, plan):
         """frames [T,3,H,W] uint8/float (0..255) on device -> normalised, zero-padded channels-last [T,3,Hp,Wp]."""
+        if self.native_gemm and self.swin is None and frames.dtype in (torch.uint8, torch.float32):
+            return RawFrames(frames.contiguous(), plan)            # the tensor-core stem normalises + pads itself
         if self.native:
             from .. import fused
             x = fused.preprocess(frames.contiguous(), self._mean3, self._std3, plan.Hp, plan.Wp, out_dtype=self.bb_dtype)
@@ -396,7 +406,13 @@ class SeqFormerEngine:
     def backbone_native(self, x):
         """NHWC throughout; 1x1 convs are tcgen05 GEMMs with fused bias/ReLU/residual epilogues."""
         from .. import fused
-        y = F.conv2d(x, self._w(self.stem[0], x.dtype, True), None, stride=2, padding=3).permute(0, 2, 3, 1)
+        if isinstance(x, RawFrames):       # 7x7 stride-2 stem as a tcgen05 implicit GEMM straight from the raw frames
+            if getattr(self, "_stem_packed", None) is None:
+                self._stem_packed = fused.pack_stem_weight(self.stem[0])
+            y = fused.stem_conv7x7(x.frames, self._stem_packed, self._mean3, self._std3, x.plan.Hp, x.plan.Wp,
+                                   out_dtype=self.bb_dtype)
+        else:
+            y = F.conv2d(x, self._w(self.stem[0], x.dtype, True), None, stride=2, padding=3).permute(0, 2, 3, 1)
         x = fused.stem_pool(y, self.stem[1])                                   # [T, H/4, W/4, 64]
         feats = {}
         for name, blocks in self.stages:
