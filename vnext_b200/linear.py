@@ -60,7 +60,7 @@ def linear(x, weight, bias=None, relu=False, gelu=False, residual=None, ln_weigh
     tag = "tf32" if x.dtype == torch.float32 else "bf16"
     with torch.cuda.device(x.device):
         rc = _cabi.timed_call(
-            name or f"linear_{tag}_n{N}_k{K}_f{flags}", info, x,
+            name or f"linear_{tag}_m{M}_n{N}_k{K}_f{flags}", info, x,
             lambda: _cabi.lib().vnext_linear_tc(
                 _DT[x.dtype], _DT[out.dtype], x2.data_ptr(), x2.stride(0), weight.data_ptr(), _ptr(bias), _ptr(bias2d), period,
                 0 if bias2d is None else bias2d.stride(0), _ptr(row_mask), int(mask_cols), _ptr(res2),
