@@ -635,6 +635,8 @@ def train_arm(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from vnext_b200.hostcfg import tune_host_threads
+    tune_host_threads(ranks_on_host=world)          # see own_arm: the step is host-heavy, 64 spinning threads on a 16-CPU quota
     seq = args.workload == "seqformer_train"
     NF, H, W = WORKLOADS[args.workload]
     host = torch.stack(synthetic_clip(NF, H, W, rank)).to(torch.uint8).pin_memory()

@@ -325,8 +325,11 @@ class IDOLTrainModel(nn.Module):
             srcs.append(s.permute(0, 2, 3, 1).flatten(1, 2))                       # a view when s is channels-last
             masks.append(m)
             poses.append(pos + self.P[TR + "level_embed"][l].view(1, 1, -1))
-        shapes = torch.as_tensor([m.shape[-2:] for m in masks], dtype=torch.long, device=self.device)
+        level_hw = [tuple(m.shape[-2:]) for m in masks]
+        shapes = torch.as_tensor(level_hw, dtype=torch.long, device=self.device)
         lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+        from ..msda import attach_host_geometry
+        attach_host_geometry(shapes, lsi, level_hw)          # the self-attention MSDA kernel plans its tiles on the host
         src = torch.cat(srcs, 1)
         pos = torch.cat(poses, 1)
         pad = torch.cat([m.flatten(1) for m in masks], 1)
@@ -336,7 +339,7 @@ class IDOLTrainModel(nn.Module):
             if frames_per_video > 1:
                 vr = vr[0::frames_per_video].repeat_interleave(frames_per_video, 0)
             refs = []
-            for l, (h, w) in enumerate(shapes.tolist()):
+            for l, (h, w) in enumerate(level_hw):
                 ry, rx = torch.meshgrid(torch.linspace(0.5, h - 0.5, h, device=self.device),
                                         torch.linspace(0.5, w - 0.5, w, device=self.device), indexing="ij")
                 refs.append(torch.stack((rx.reshape(-1)[None] / (vr[:, None, l, 0] * w),

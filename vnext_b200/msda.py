@@ -87,6 +87,15 @@ def host_geometry(spatial_shapes, level_start_index):
     return hit[1], hit[2]
 
 
+def attach_host_geometry(spatial_shapes, level_start_index, level_hw):
+    """A caller that built the two geometry tensors from host integers registers them here: no device sync later."""
+    import numpy as np
+    hs = np.asarray(level_hw, dtype=np.int64).reshape(-1, 2).copy()
+    starts = np.concatenate(([0], np.cumsum(hs[:, 0] * hs[:, 1])[:-1])).astype(np.int64)
+    tag = (spatial_shapes._version, id(level_start_index), level_start_index._version)
+    spatial_shapes._vnext_host_geom = (tag, hs, starts, level_start_index)
+
+
 def _selfattn_margin(value):
     return -1 if WINDOW_MODE == "cached" else WINDOW_MARGIN[value.dtype]
 
