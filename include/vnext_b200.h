@@ -285,6 +285,12 @@ int vnext_layernorm(const float *x, const float *gamma, const float *beta, float
  * its residual stream in fp32 and hands bf16 tensors to / takes them from the bf16 GEMMs. */
 int vnext_swin_window_attention_tc_dt(int io_dtype, const void *qkv, const float *qkv_bias, const float *rel_pos_bias_table,
                                       void *out, int B, int H, int W, int C, int heads, int window, int shift, void *stream);
+/* bf16 storage, register-resident (flash-attention style) kernel: a warp owns 16 query rows, S / P / O never leave the register
+ * file, both products are mma.sync m16n8k16 bf16 MMAs (csrc/swin_attention_mma.cu says why this beats the TMEM round trip at
+ * 144 x 144 x 32).  qkv / out bf16; window in [2, 12].
+ * NB: takes the relative-position-bias table TRANSPOSED, [heads, (2*window-1)^2] (one coalesced row per head). */
+int vnext_swin_window_attention_bf16(const void *qkv, const float *qkv_bias, const float *rel_pos_bias_table_t, void *out, int B,
+                                     int H, int W, int C, int heads, int window, int shift, void *stream);
 int vnext_layernorm_dt(int in_dtype, int out_dtype, const void *x, const float *gamma, const float *beta, void *out,
                        long long rows, int C, float eps, void *stream);
 

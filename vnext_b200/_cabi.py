@@ -52,6 +52,7 @@ SIGNATURES = {
     "vnext_swin_window_attention_tc": (_c_int, [_c_void_p] * 4 + [_c_int] * 7 + [_c_void_p]),
     "vnext_layernorm": (_c_int, [_c_void_p] * 4 + [ctypes.c_longlong, _c_int, ctypes.c_float, _c_void_p]),
     "vnext_layernorm_dt": (_c_int, [_c_int, _c_int] + [_c_void_p] * 4 + [ctypes.c_longlong, _c_int, ctypes.c_float, _c_void_p]),
+    "vnext_swin_window_attention_bf16": (_c_int, [_c_void_p] * 4 + [_c_int] * 7 + [_c_void_p]),
     "vnext_swin_window_attention_tc_dt": (_c_int, [_c_int] + [_c_void_p] * 4 + [_c_int] * 7 + [_c_void_p]),
     "vnext_adamw": (_c_int, [_c_void_p] * 4 + [ctypes.c_longlong] + [ctypes.c_float] * 7 + [_c_void_p, _c_void_p]),
     "vnext_dynamic_mask_head": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p] + [_c_int] * 5 + [_c_void_p]),

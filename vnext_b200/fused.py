@@ -1,6 +1,7 @@
 """Python face of the single-pass NHWC kernels (include/vnext_b200.h: vnext_bias_act, vnext_stem_pool,
 vnext_groupnorm_nhwc, vnext_preprocess).  CUDA only."""
 import ctypes
+import os
 
 import torch
 
@@ -132,8 +133,18 @@ def swin_window_attention(qkv, qkv_bias, table, heads, window, shift, tensor_cor
     e = qkv.element_size()
     info = {"bytes": float(e) * (qkv.numel() + out.numel()), "flops": 4.0 * B * (-(-H // window)) * (-(-W // window)) * heads * n * n * 32}
     tc = tensor_cores and window >= 4
+    if qkv.dtype == torch.bfloat16 and os.environ.get("VNEXT_SWIN_BF16_KERNEL", "mma") == "mma":
+        # bf16 storage: the register-resident mma.sync kernel (csrc/swin_attention_mma.cu)
+        tt = getattr(table, "_vnext_t", None)                     # [heads, (2ws-1)^2]: transposed once per table tensor
+        if tt is None or tt[0] != table._version:
+            tt = (table._version, table.t().contiguous())
+            table._vnext_t = tt
+        rc = _cabi.timed_call("swin_window_attention_bf16", info, qkv, lambda: _cabi.lib().vnext_swin_window_attention_bf16(
+            qkv.data_ptr(), qkv_bias.data_ptr(), tt[1].data_ptr(), out.data_ptr(), B, H, W, C, heads, window, shift, _st(qkv)))
+        _cabi.check(rc, "vnext_swin_window_attention_bf16")
+        return out
     if not tc and qkv.dtype != torch.float32:
-        raise RuntimeError("swin_window_attention: bf16 storage needs the tensor-core kernel (window >= 4)")
+        raise RuntimeError("swin_window_attention: bf16 storage needs a tensor-core kernel")
     if tc:
         call = lambda: _cabi.lib().vnext_swin_window_attention_tc_dt(
             _DT[qkv.dtype], qkv.data_ptr(), qkv_bias.data_ptr(), table.data_ptr(), out.data_ptr(), B, H, W, C, heads, window, shift, _st(qkv))
