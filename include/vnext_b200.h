@@ -228,6 +228,9 @@ int vnext_mha_small(const float *qkv, int ld, float *out, int ldo, int batch, in
 int vnext_time_pool_ln(const float *out_in, const float *t2, const float *logit, const float *gamma, const float *beta,
                        float *out, int T, int nq, int C, float eps, void *stream);
 int vnext_box_refine(const float *delta, const float *ref, float *out, int rows, int ref_dim, void *stream);
+/* out[r,0:2] = sigmoid(inverse_sigmoid(ref[r,0:2])) * (scale_w, scale_h): reference points in pixels for the dynamic mask head
+ * (projects/SeqFormer/seqformer/models/segmentation_condInst.py:311-331). */
+int vnext_ref_points_px(const float *ref, float *out, int rows, int ref_dim, float scale_w, float scale_h, void *stream);
 
 /*
  * Single-pass NHWC epilogues of the backbone / input projection (fp32, C % 4 == 0, 16-byte aligned):

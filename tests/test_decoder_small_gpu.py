@@ -59,3 +59,15 @@ def test_box_refine(ref_dim):
         want = torch.cat([delta[..., :2] + inverse_sigmoid(ref), delta[..., 2:]], -1).sigmoid()
     got = fused.box_refine(delta, ref.expand(5, 300, ref_dim))
     assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+def test_ref_points_px(ref_dim):
+    from vnext_b200 import fused
+    from vnext_b200.seqformer.engine import inverse_sigmoid
+    ref = torch.rand(5, 300, ref_dim, generator=torch.Generator().manual_seed(1)).cuda()
+    ref[0, 0] = 0.0
+    ref[0, 1] = 1.0
+    want = inverse_sigmoid(ref)[..., :2].sigmoid() * torch.tensor([1280.0, 720.0], device="cuda")
+    got = fused.ref_points_px(ref, 1280.0, 720.0)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-3)

@@ -33,6 +33,7 @@ SIGNATURES = {
     "vnext_conv3x3_tc": (_c_int, [_c_int, _c_int] + [_c_void_p] * 4 + [_c_int] * 6 + [_c_void_p]),
     "vnext_conv3x3_strided_tc": (_c_int, [_c_int, _c_int] + [_c_void_p] * 4 + [_c_int] * 7 + [_c_void_p]),
     "vnext_time_pool_ln": (_c_int, [_c_void_p] * 6 + [_c_int] * 3 + [ctypes.c_float, _c_void_p]),
+    "vnext_ref_points_px": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, ctypes.c_float, ctypes.c_float, _c_void_p]),
     "vnext_box_refine": (_c_int, [_c_void_p] * 3 + [_c_int] * 2 + [_c_void_p]),
     "vnext_stem_conv7x7": (_c_int, [_c_int, _c_int] + [_c_void_p] * 5 + [_c_int] * 6 + [_c_void_p, _c_void_p, _c_int, _c_void_p]),
     "vnext_mha_small": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p]),

@@ -65,6 +65,17 @@ __global__ void box_refine_kernel(const float *__restrict__ delta, const float *
     out[i] = 1.f / (1.f + expf(-x));
 }
 
+// ref_px[r, 0:2] = sigmoid(inverse_sigmoid(ref[r, 0:2])) * (scale_w, scale_h): the reference points of the last decoder level
+// in pixels, as the mask head wants them (segmentation_condInst.py:311-331: inverse_sigmoid -> sigmoid -> scale)
+__global__ void ref_points_px_kernel(const float *__restrict__ ref, float *__restrict__ out, int rows, int ref_dim, float sw,
+                                     float sh) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * 2) return;
+    const int r = i >> 1, k = i & 1;
+    const float x = inverse_sigmoid_f(ref[r * ref_dim + k]);
+    out[i] = (1.f / (1.f + expf(-x))) * (k ? sh : sw);
+}
+
 }  // namespace vnext
 
 using namespace vnext;
@@ -86,6 +97,16 @@ extern "C" int vnext_box_refine(const float *delta, const float *ref, float *out
     if (rows == 0) return VNEXT_OK;
     VNEXT_CHECK_ARG(delta && ref && out, "vnext_box_refine: null pointer");
     box_refine_kernel<<<(rows * 4 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(delta, ref, out, rows, ref_dim);
+    count_launch();
+    VNEXT_CUDA(cudaGetLastError());
+    return VNEXT_OK;
+}
+
+extern "C" int vnext_ref_points_px(const float *ref, float *out, int rows, int ref_dim, float scale_w, float scale_h, void *stream) {
+    VNEXT_CHECK_ARG(rows >= 0 && (ref_dim == 2 || ref_dim == 4), "vnext_ref_points_px: ref_dim must be 2 or 4");
+    if (rows == 0) return VNEXT_OK;
+    VNEXT_CHECK_ARG(ref && out, "vnext_ref_points_px: null pointer");
+    ref_points_px_kernel<<<(rows * 2 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(ref, out, rows, ref_dim, scale_w, scale_h);
     count_launch();
     VNEXT_CUDA(cudaGetLastError());
     return VNEXT_OK;

@@ -15,6 +15,11 @@
 
 namespace vnext {
 
+// sigmoid(v) > 0.5 (seqformer.py:388-396: sigmoid, then `> 0.5`) without the exponential: the two differ only for
+// 0 < v < 6e-8, where fp32 sigmoid rounds to exactly 0.5
+__device__ __forceinline__ bool mask_on(float v) { return v > 0.f; }
+
+
 constexpr int kMhThreads = 256;
 
 // feats [T, H, W, 8] (NHWC); params [n, 169] (pstride_t = 0) or [T, n, 169]; ref_px [T, n, 2] (x, y) in pixels
@@ -113,8 +118,7 @@ __global__ void __launch_bounds__(256) mask_finalize_kernel(const float *__restr
             const float v00 = logit4(m, H8, W8, y0, x0), v01 = logit4(m, H8, W8, y0, x1);
             const float v10 = logit4(m, H8, W8, y1, x0), v11 = logit4(m, H8, W8, y1, x1);
             const float v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
-            const float sg = 1.f / (1.f + expf(-v));
-            if (sg > 0.5f) word[k / 4] |= 1u << (8 * (k % 4));
+            if (mask_on(v)) word[k / 4] |= 1u << (8 * (k % 4));
         }
         unsigned int *o = reinterpret_cast<unsigned int *>(out + ((size_t)(img * (long long)OH + Y) * OW + (size_t)Xg * PIX));
 #pragma unroll
@@ -154,7 +158,7 @@ __global__ void __launch_bounds__(256) mask_finalize_x4_kernel(const float *__re
             float lx = kLx[k];
             if (g == 0 && k < 2) lx = 0.f;                        // src_x clamped at 0 on the left edge
             const float v = col[j0] + (col[j0 + 1] - col[j0]) * lx;
-            const unsigned int bit = (1.f / (1.f + expf(-v))) > 0.5f ? 1u : 0u;
+            const unsigned int bit = mask_on(v) ? 1u : 0u;
             if (k < 4) w0 |= bit << (8 * k); else w1 |= bit << (8 * (k - 4));
         }
         *reinterpret_cast<uint2 *>(out + ((size_t)(img * (long long)H + y) * W + (size_t)g * 8)) = make_uint2(w0, w1);
@@ -181,7 +185,7 @@ __global__ void __launch_bounds__(256) mask_finalize_scalar_kernel(const float *
         const float *m = p8 + (size_t)img * H8 * W8;
         const float v = (1.f - ly) * ((1.f - lx) * logit4(m, H8, W8, y0, x0) + lx * logit4(m, H8, W8, y0, x1)) +
                         ly * ((1.f - lx) * logit4(m, H8, W8, y1, x0) + lx * logit4(m, H8, W8, y1, x1));
-        out[e] = (1.f / (1.f + expf(-v))) > 0.5f ? 1 : 0;
+        out[e] = mask_on(v) ? 1 : 0;
     }
 }
 

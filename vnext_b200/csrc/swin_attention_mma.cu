@@ -170,6 +170,12 @@ __global__ void __launch_bounds__(kMmMaxWarps * 32, 2) swin_window_attention_mma
         const int c0 = st.code[min(r0, N - 1)], c1 = st.code[min(r1, N - 1)];
         const int off = (ws - 1) * (2 * ws - 1) + (ws - 1);
         const int ib0 = (c0 >> 4) + off, ib1 = (c1 >> 4) + off, ireg0 = c0 & 15, ireg1 = c1 & 15;
+        bool masked = false;                   // does this window straddle shift regions at all?
+        if (p.shift > 0) {
+            int bid2 = item / p.heads;
+            const int wx2 = bid2 % nWx, wy2 = (bid2 / nWx) % nWy;
+            masked = wx2 == nWx - 1 || wy2 == nWy - 1;
+        }
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
         for (int j = 0; j < kMmMaxTiles; ++j) {
@@ -183,8 +189,10 @@ __global__ void __launch_bounds__(kMmMaxWarps * 32, 2) swin_window_attention_mma
                         const int kb = jc >> 4, kr = jc & 15;
                         float a = fmaf(s[j][e], p.scale, st.bias[ib0 - kb]);
                         float c = fmaf(s[j][2 + e], p.scale, st.bias[ib1 - kb]);
-                        if (kr != ireg0) a += -100.0f;
-                        if (kr != ireg1) c += -100.0f;
+                        if (masked) {              // (uniform per item: only the last window row / column of a shifted block)
+                            if (kr != ireg0) a += -100.0f;
+                            if (kr != ireg1) c += -100.0f;
+                        }
                         s[j][e] = a; s[j][2 + e] = c;
                         mx0 = fmaxf(mx0, a); mx1 = fmaxf(mx1, c);
                     } else {

@@ -179,6 +179,17 @@ def box_refine(delta, ref):
     return out
 
 
+def ref_points_px(ref, scale_w, scale_h):
+    """ref [..., 2|4] in [0, 1] -> sigmoid(inverse_sigmoid(ref[..., :2])) * (scale_w, scale_h)  [..., 2]."""
+    ref = ref.contiguous()
+    out = torch.empty(ref.shape[:-1] + (2,), dtype=torch.float32, device=ref.device)
+    rows = out.numel() // 2
+    rc = _cabi.timed_call("ref_points_px", {"bytes": 4.0 * (ref.numel() + out.numel())}, ref, lambda: _cabi.lib().vnext_ref_points_px(
+        ref.data_ptr(), out.data_ptr(), rows, ref.shape[-1], float(scale_w), float(scale_h), _st(ref)))
+    _cabi.check(rc, "vnext_ref_points_px")
+    return out
+
+
 def small_mha(qkv, heads):
     """qkv [B, n, 3*heads*32] fp32 (rows may be strided) -> softmax(q k^T / sqrt(32)) v, heads merged: [B, n, heads*32]."""
     B, n, C3 = qkv.shape

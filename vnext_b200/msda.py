@@ -78,7 +78,7 @@ def host_geometry(spatial_shapes, level_start_index):
     tag = (spatial_shapes._version, id(level_start_index), level_start_index._version)
     hit = getattr(spatial_shapes, "_vnext_host_geom", None)
     if hit is None or hit[0] != tag:
-        if torch.cuda.is_current_stream_capturing():
+        if spatial_shapes.is_cuda and torch.cuda.is_current_stream_capturing():
             raise RuntimeError("ms_deform_attn: spatial_shapes must be known on the host before CUDA-graph capture "
                                "(call msda.host_geometry(shapes, lsi) once outside the capture)")
         hit = (tag, spatial_shapes.cpu().numpy().astype("int64").copy(), level_start_index.cpu().numpy().astype("int64").copy(),

@@ -547,7 +547,9 @@ class SeqFormerEngine:
         levels = []
         for lid, w in enumerate(self.dec):
             if ref.shape[-1] == 4:
-                ref_in = ref[:, :, None] * torch.cat([vr, vr], -1)[:, None]
+                if "vr4" not in plan.extra:
+                    plan.extra["vr4"] = torch.cat([vr, vr], -1)
+                ref_in = ref[:, :, None] * plan.extra["vr4"][:, None]
             else:
                 ref_in = ref[:, :, None] * vr[:, None]
             a = w["attn"]
@@ -600,20 +602,29 @@ class SeqFormerEngine:
         """class / box / controller heads of one decoder level (segmentation_condInst.py:311-331)."""
         lid, hs, hs_box, prev_ref = level
         w = self.dec[lid]
-        reference = inverse_sigmoid(prev_ref)                    # [T, nq, 2|4]
+        fast = self.native_gemm and prev_ref.dtype == torch.float32
+        reference = None if fast else inverse_sigmoid(prev_ref)  # [T, nq, 2|4]
         logits = self.lin(hs, w["cls"])                          # [1, nq, K]
         tmp = hs_box
         for j, wb in enumerate(w["bbox"]):
             tmp = self.lin(tmp, wb, relu=(j < 2))
-        if reference.shape[-1] == 4:
-            tmp = tmp + reference
+        if self.native_gemm and tmp.dtype == torch.float32:      # sigmoid(tmp + inverse_sigmoid(prev_ref)): one kernel
+            from .. import fused
+            boxes = fused.box_refine(tmp, prev_ref)
         else:
-            tmp = torch.cat([tmp[..., :2] + reference, tmp[..., 2:]], -1)
-        boxes = tmp.sigmoid()                                    # [T, nq, 4]
+            if reference.shape[-1] == 4:
+                tmp = tmp + reference
+            else:
+                tmp = torch.cat([tmp[..., :2] + reference, tmp[..., 2:]], -1)
+            boxes = tmp.sigmoid()                                # [T, nq, 4]
         params = hs
         for j, wb in enumerate(self.controller):
             params = self.lin(params, wb, relu=(j < 2))
-        ref_px = reference[..., :2].sigmoid() * plan.extra["scale_wh"]   # [T, nq, 2] in pixels
+        if fast:
+            from .. import fused
+            ref_px = fused.ref_points_px(prev_ref, float(plan.W), float(plan.H))
+        else:
+            ref_px = reference[..., :2].sigmoid() * plan.extra["scale_wh"]   # [T, nq, 2] in pixels
         return logits, boxes, params[0], ref_px
 
     def mask_features(self, memory, plan):
