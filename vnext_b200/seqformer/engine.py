@@ -113,6 +113,7 @@ class SeqFormerEngine:
         self.act_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
         import os
         self._small_fp32 = os.environ.get("VNEXT_SMALL_FP32", "0") == "1"
+        self._two_stream_decoder = os.environ.get("VNEXT_TWO_STREAM_DECODER", "1") == "1"
         parts = os.environ.get("VNEXT_BF16_PARTS", "backbone,encoder").split(",")     # experiment switch (tools/bf16_error_budget.py)
         self.bb_dtype = self.act_dtype if "backbone" in parts else torch.float32      # backbone + input projection storage
         self.val_dtype = self.act_dtype if ("encoder" in parts or "value" in parts) else torch.float32    # MSDA value / sampled
@@ -552,6 +553,51 @@ class SeqFormerEngine:
                 ref_in = ref[:, :, None] * plan.extra["vr4"][:, None]
             else:
                 ref_in = ref[:, :, None] * vr[:, None]
+            a = w["attn"]
+            if self.native_gemm and out.dtype == torch.float32 and self._two_stream_decoder:
+                # The clip-level (mask) stream and the per-frame (box) stream of a layer only meet at the sampler's inputs and at
+                # the temporal pooling: their chains of small launch-latency-bound kernels run on TWO CUDA streams (fork / join by
+                # events; captured into the same graph).  Every region on `bx` starts by waiting for `main`, so a tensor freed
+                # on one stream is never re-used before the other stream's reads of it were enqueued.
+                from .. import fused
+                main = torch.cuda.current_stream(self.device)
+                if getattr(self, "_box_stream", None) is None:
+                    self._box_stream = torch.cuda.Stream(device=self.device)
+                bx = self._box_stream
+                bx.wait_stream(main)
+                with torch.cuda.stream(bx):
+                    out_box = self._mha_self(out_box, w["self_attn_box"], (lid, "sab"), w["norm2_box"])
+                    oa = self.lin(out_box, (a["oa_w"], None), bias2d=self._qpos_bias((lid, "oa"), a["oa_w"], a["oa_b"]))
+                out = self._mha_self(out, w["self_attn"], (lid, "sa"), w["norm2"])
+                main.wait_stream(bx)
+                oa = oa.expand(T, -1, -1)
+                if branches is not None:
+                    main.wait_event(branches["value_events"][lid])
+                    value = branches["values"][lid]
+                else:
+                    value = self._value(memory, a, plan)
+                s = self.sample(value, oa, ref_in, plan, a["n_off"]).float()   # [T, nq, C]
+                bx.wait_stream(main)
+                with torch.cuda.stream(bx):                          # box stream: projection, FFN, time logits, box head
+                    out_box = self.lin(s, (a["ob_w"][C:], a["ob_b"][C:]), residual=out_box.expand(T, -1, -1), ln=w["norm1_box"])
+                    out_box = self.lin(self.lin(out_box, w["linear1_box"], relu=True), w["linear2_box"], residual=out_box,
+                                       ln=w["norm3_box"])
+                    twl = self.lin(out_box, w["time_attention_weights"]).contiguous()
+                    ev_tw = torch.cuda.Event()
+                    ev_tw.record(bx)
+                    tmp = out_box
+                    for j, wb in enumerate(w["bbox"]):
+                        tmp = self.lin(tmp, wb, relu=(j < 2))
+                    prev_ref = ref
+                    ref = fused.box_refine(tmp, ref)
+                t2 = self.lin(s, (a["o_w"], a["o_b"]))               # mask stream: projection, temporal pooling, FFN
+                main.wait_event(ev_tw)
+                out = fused.time_pool_ln(out.contiguous(), t2.contiguous(), twl, *w["norm1"])
+                out = self.lin(self.lin(out, w["linear1"], relu=True), w["linear2"], residual=out, ln=w["norm3"])
+                main.wait_stream(bx)
+                if collect_all or lid == len(self.dec) - 1:
+                    levels.append((lid, out, out_box, prev_ref))
+                continue
             a = w["attn"]
             if self.native_gemm and out.dtype == torch.float32:
                 out = self._mha_self(out, w["self_attn"], (lid, "sa"), w["norm2"])
