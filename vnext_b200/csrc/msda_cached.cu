@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(kCachedThreads, 1) msda_fwd_cached_kernel(cons
                     const float2 off = ldg_stream_f2(rowp + (s.m * LK + smp) * 2);
                     in.a0 = off.x; in.a1 = off.y;
                     in.a2 = ldg_stream_f1(rowp + p.n_off + s.m * LK + smp);
-                    const float2 rf = __ldg(reinterpret_cast<const float2 *>(
-                        p.ref + s.n * p.ref_batch_stride + ((size_t)(s.row - s.n * p.S) * p.L + lvl) * 2));
+                    // (no L1 allocation either: the reference grid is 0.6 MB per frame set and would evict corner rows)
+                    const float2 rf = ldg_stream_f2(p.ref + s.n * p.ref_batch_stride + ((size_t)(s.row - s.n * p.S) * p.L + lvl) * 2);
                     in.r0 = rf.x; in.r1 = rf.y;
                 } else {
                     const size_t si = ((size_t)s.row * p.M + s.m) * LK + smp;

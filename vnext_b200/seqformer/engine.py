@@ -585,11 +585,12 @@ class SeqFormerEngine:
                     twl = self.lin(out_box, w["time_attention_weights"]).contiguous()
                     ev_tw = torch.cuda.Event()
                     ev_tw.record(bx)
-                    tmp = out_box
-                    for j, wb in enumerate(w["bbox"]):
-                        tmp = self.lin(tmp, wb, relu=(j < 2))
                     prev_ref = ref
-                    ref = fused.box_refine(tmp, ref)
+                    if lid < len(self.dec) - 1:                      # (the last layer's refined boxes feed nothing)
+                        tmp = out_box
+                        for j, wb in enumerate(w["bbox"]):
+                            tmp = self.lin(tmp, wb, relu=(j < 2))
+                        ref = fused.box_refine(tmp, ref)
                 t2 = self.lin(s, (a["o_w"], a["o_b"]))               # mask stream: projection, temporal pooling, FFN
                 main.wait_event(ev_tw)
                 out = fused.time_pool_ln(out.contiguous(), t2.contiguous(), twl, *w["norm1"])
@@ -644,17 +645,21 @@ class SeqFormerEngine:
                 levels.append((lid, out, out_box, prev_ref))
         return levels
 
-    def heads(self, level, plan):
-        """class / box / controller heads of one decoder level (segmentation_condInst.py:311-331)."""
+    def heads(self, level, plan, need_boxes=True):
+        """class / box / controller heads of one decoder level (segmentation_condInst.py:311-331).  need_boxes=False: the
+        video-level post-processing (seqformer.py:363-410) reads class scores and masks only — the box head is skipped."""
         lid, hs, hs_box, prev_ref = level
         w = self.dec[lid]
         fast = self.native_gemm and prev_ref.dtype == torch.float32
         reference = None if fast else inverse_sigmoid(prev_ref)  # [T, nq, 2|4]
         logits = self.lin(hs, w["cls"])                          # [1, nq, K]
         tmp = hs_box
-        for j, wb in enumerate(w["bbox"]):
+        boxes = None
+        for j, wb in enumerate(w["bbox"] if need_boxes else ()):
             tmp = self.lin(tmp, wb, relu=(j < 2))
-        if self.native_gemm and tmp.dtype == torch.float32:      # sigmoid(tmp + inverse_sigmoid(prev_ref)): one kernel
+        if not need_boxes:
+            pass
+        elif self.native_gemm and tmp.dtype == torch.float32:    # sigmoid(tmp + inverse_sigmoid(prev_ref)): one kernel
             from .. import fused
             boxes = fused.box_refine(tmp, prev_ref)
         else:
@@ -828,7 +833,7 @@ class SeqFormerEngine:
         memory = self.encoder(self.tokens(feats, plan), plan)
         br = self.memory_branches(memory, plan)
         level = self.decoder(memory, plan, branches=br)[-1]
-        logits, boxes, params, ref_px = self.heads(level, plan)
+        logits, _, params, ref_px = self.heads(level, plan, need_boxes=False)
         scores = logits[0].sigmoid()
         k = min(topk, scores.shape[0])
         _, idx = torch.topk(scores.max(1)[0], k=k)
