@@ -98,6 +98,10 @@ int vnext_msda_forward_fused(int dtype, const void *value, const int64_t *spatia
  *   them per call); levels must tile [0, spatial_size) in order.
  *   Front-end: either (sampling_loc, attn_weight) as vnext_msda_forward, or — when offsets_logits != NULL — the fused
  *   one of vnext_msda_forward_fused (offsets_logits, row_pitch, reference_points, ref_dim == 2, ref_shared).
+ *   margin >= 0: the shared-memory window kernel (csrc/msda_window.cu) with that margin; margin < 0: the cache-blocked kernel
+ *   (csrc/msda_cached.cu: 2-D query tiles x head, the L1 does the staging).  With margin < 0, offsets_logits != NULL and
+ *   reference_points == NULL mean the rows already hold sampling LOCATIONS | normalised attention WEIGHTS in the same layout
+ *   (what vnext_linear_msda_front writes): no front-end arithmetic in the sampler.
  * Needs channels == 32, num_levels <= 4, num_levels*num_point in {8, 16, 32}, value fp32 or bf16 (16-byte aligned).
  */
 int vnext_msda_forward_selfattn(int dtype, const void *value, const int64_t *spatial_shapes_host,
@@ -175,6 +179,17 @@ int vnext_linear_tc(int in_dtype, int out_dtype, const void *a, int lda, const v
                     const float *bias2d, int bias_period, int ldb2, const unsigned char *row_mask, int mask_cols,
                     const void *residual, int ldr, const float *ln_gamma, const float *ln_beta, float ln_eps, void *out,
                     int ldo, int M, int N, int K, int flags, void *stream);
+
+/*
+ * The encoder's offsets | logits projection with the sampler's front-end fused into the epilogue (N = 384 = 8 heads x (4 levels
+ * x 4 points x 2 | 4 x 4)): out[row, 0:256] = reference_points[row % period, level, xy] + (a W^T + bias2d)[.] / (W_level | H_level),
+ * out[row, 256:384] = softmax over each head's 16 logits — MSDeformAttn.forward between its two Linears and the sampling op
+ * (projects/IDOL/idol/models/ops/modules/ms_deform_attn.py:98-108).  reference_points [period, 4, 2] fp32, level_wh = HOST
+ * pointer to (W_0, H_0, ..., W_3, H_3) as floats; bias2d [period, 384] (row-periodic, carries the projection bias); out fp32.
+ */
+int vnext_linear_msda_front(int in_dtype, const void *a, int lda, const void *weight, const float *bias2d, int bias_period,
+                            int ldb2, const float *reference_points, const float *level_wh, float *out, int ldo, int M, int K,
+                            void *stream);
 
 /*
  * 3x3 convolution, stride 1, zero padding 1, NHWC fp32, as an implicit GEMM on the tcgen05 tensor cores (TF32) with

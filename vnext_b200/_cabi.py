@@ -30,6 +30,8 @@ SIGNATURES = {
     "vnext_linear_tc": (_c_int, [_c_int, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p,
                                  _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, ctypes.c_float, _c_void_p, _c_int,
                                  _c_int, _c_int, _c_int, _c_int, _c_void_p]),
+    "vnext_linear_msda_front": (_c_int, [_c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p,
+                                         _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
     "vnext_conv3x3_tc": (_c_int, [_c_int, _c_int] + [_c_void_p] * 4 + [_c_int] * 6 + [_c_void_p]),
     "vnext_conv3x3_strided_tc": (_c_int, [_c_int, _c_int] + [_c_void_p] * 4 + [_c_int] * 7 + [_c_void_p]),
     "vnext_time_pool_ln": (_c_int, [_c_void_p] * 6 + [_c_int] * 3 + [ctypes.c_float, _c_void_p]),

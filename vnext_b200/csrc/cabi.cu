@@ -124,7 +124,8 @@ int vnext_msda_forward_selfattn(int dtype, const void *value, const int64_t *spa
     if (rc) return rc;
     const bool empty = (long long)batch * spatial_size == 0;
     VNEXT_CHECK_ARG(empty || (value && spatial_shapes_host && level_start_index_host && output &&
-                              ((sampling_loc && attn_weight) || (offsets_logits && reference_points))),
+                              ((sampling_loc && attn_weight) || (offsets_logits && reference_points) ||
+                               (offsets_logits && margin < 0))),
                     "vnext_msda_forward_selfattn: null tensor pointer");
     VNEXT_CHECK_ARG(channels == 32 && msda_window_supported(dtype, channels, num_levels, num_point),
                     "vnext_msda_forward_selfattn: needs channels == 32, num_levels <= 4, num_levels*num_point in {8,16,32}, "

@@ -168,6 +168,11 @@ struct GemmParams {
     const float *bias2d;     // [period, ldb2] or null: added as bias2d[row % period][col] (geometry-dependent bias)
     int period, ldb2;
     int pdl;                 // launched with programmatic stream serialization (see the kernel prologue)
+    // MSDA front-end in the epilogue (N == 384 = 8 heads x (4 levels x 4 points x 2 offsets | 4 x 4 logits)): the offsets
+    // columns become sampling locations ref + off / (W_l, H_l), the logits columns the softmax over each head's 16 — what
+    // MSDeformAttn.forward does between its projection and the sampler (ops/modules/ms_deform_attn.py:98-108)
+    const float *msda_ref;   // [period, 4 levels, 2] reference points (row % period), or null
+    float msda_wh[8];        // (1/W_0, 1/H_0, ..., 1/W_3, 1/H_3)
     int b2_tma;              // the 2-D bias tile comes through shared memory (four 8-row TMA boxes, rows taken mod period)
     const unsigned char *row_mask;   // [period] or null: rows with mask != 0 get columns [0, mask_cols) zeroed
     int mask_cols;
@@ -458,6 +463,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                             if (lane == 0 && c + 2 < n_chunks) load_addend(col0 + 64, row0);
                         }
                         if ((p.bias2d && !b2_tma) || (has_res && !rrow)) epilogue_add_global(p, row, row_ok, col0, v);
+                        if (p.msda_ref && row_ok) {
+                            if (col0 < 256) {        // column = ((head*4 + level)*4 + point)*2 + xy  ->  level = (j >> 3) & 3
+                                const float4 ra = *reinterpret_cast<const float4 *>(p.msda_ref + (size_t)(row % p.period) * 8);
+                                const float4 rb = *reinterpret_cast<const float4 *>(p.msda_ref + (size_t)(row % p.period) * 8 + 4);
+                                const float rf[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    const int k = ((j >> 3) & 3) * 2 + (j & 1);
+                                    v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), p.msda_wh[k], rf[k]));
+                                }
+                            } else {                 // two heads' 16 logits each: softmax in registers
+#pragma unroll
+                                for (int hh = 0; hh < 2; ++hh) {
+                                    float mx = -INFINITY;
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(v[hh * 16 + j]));
+                                    float sm = 0.f;
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) {
+                                        const float e = __expf(__uint_as_float(v[hh * 16 + j]) - mx);
+                                        sm += e;
+                                        v[hh * 16 + j] = __float_as_uint(e);
+                                    }
+#pragma unroll
+                                    const float inv = __frcp_rn(sm);
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) v[hh * 16 + j] = __float_as_uint(__uint_as_float(v[hh * 16 + j]) * inv);
+                                }
+                            }
+                        }
                     }
                     if (pass == 0) {
 #pragma unroll
@@ -730,6 +765,8 @@ struct LinearArgs {
     const float *gamma, *beta; float eps;
     void *out; int ldo;
     int M, N, K, flags;
+    const float *msda_ref = nullptr;       // see GemmParams::msda_ref
+    const float *msda_wh = nullptr;        // host pointer to 8 floats
 };
 
 static inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -747,6 +784,8 @@ int linear_tc_device(const LinearArgs &x, cudaStream_t stream) {
     p.conv_stride = 1;
     p.cluster = 1;
     p.pdl = 0;
+    p.msda_ref = x.msda_ref;
+    for (int i = 0; i < 8; ++i) p.msda_wh[i] = x.msda_wh ? 1.f / x.msda_wh[i] : 1.f;
     p.b2_tma = 0;
     p.vec_ok = al16(x.out) && x.ldo % oe == 0 && (!x.bias || al16(x.bias)) &&
                (!x.bias2d || (al16(x.bias2d) && x.ldb2 % 4 == 0)) && (!x.residual || (al16(x.residual) && x.ldr % oe == 0));
@@ -805,6 +844,7 @@ int conv3x3_tc_device(int in_dt, int out_dt, const void *x, const void *w, const
     p.M = T * H * W; p.N = Cout; p.K = 9 * Cin; p.bias = bias; p.bias2d = nullptr; p.period = 1; p.ldb2 = 0;
     p.b2_tma = 0;
     p.pdl = 0;
+    p.msda_ref = nullptr;
     p.row_mask = nullptr; p.mask_cols = 0; p.residual = nullptr; p.gamma = p.beta = nullptr; p.out = static_cast<float *>(out);
     p.ldo = Cout; p.ldr = 0; p.flags = relu ? EPI_RELU : 0; p.eps = 0.f; p.vec_ok = 1; p.tma_epi = 1;
     p.conv = 1; p.conv_cin_blocks = Cin / kbox; p.conv_tiles_x = (W + 15) / 16; p.conv_tiles_y = (H + 7) / 8;
@@ -838,7 +878,7 @@ int stem_conv_device(int out_dt, const float *xpad, const float *w, const float 
     const int Ho = Hp / 2, Wo = Wp / 2;
     GemmParams p;
     p.M = T * Ho * Wo; p.N = Cout; p.K = 7 * 32; p.bias = bias; p.bias2d = nullptr; p.period = 1; p.ldb2 = 0;
-    p.b2_tma = 0; p.pdl = 0;
+    p.b2_tma = 0; p.pdl = 0; p.msda_ref = nullptr;
     p.row_mask = nullptr; p.mask_cols = 0; p.residual = nullptr; p.gamma = p.beta = nullptr; p.out = static_cast<float *>(out);
     p.ldo = Cout; p.ldr = 0; p.flags = relu ? EPI_RELU : 0; p.eps = 0.f; p.vec_ok = 1; p.tma_epi = 1;
     p.conv = 2; p.conv_cin_blocks = 1; p.conv_stride = 2; p.conv_tiles_x = (Wo + 127) / 128; p.conv_tiles_y = Ho;
@@ -941,4 +981,21 @@ extern "C" int vnext_linear_tc(int in_dtype, int out_dtype, const void *a, int l
                                void *out, int ldo, int M, int N, int K, int flags, void *stream) {
     return linear_checked("vnext_linear_tc", in_dtype, out_dtype, a, lda, weight, bias, bias2d, bias_period, ldb2, row_mask,
                           mask_cols, residual, ldr, ln_gamma, ln_beta, ln_eps, out, ldo, M, N, K, flags, stream);
+}
+
+extern "C" int vnext_linear_msda_front(int in_dtype, const void *a, int lda, const void *weight, const float *bias2d, int bias_period,
+                                       int ldb2, const float *reference_points, const float *level_wh, float *out, int ldo, int M,
+                                       int K, void *stream) {
+    VNEXT_CHECK_ARG(in_dtype == VNEXT_F32 || in_dtype == VNEXT_BF16, "vnext_linear_msda_front: dtype must be fp32 (0) or bf16 (2)");
+    VNEXT_CHECK_ARG(M >= 0 && K > 0 && bias_period > 0, "vnext_linear_msda_front: bad sizes M=%d K=%d period=%d", M, K, bias_period);
+    if (M == 0) return VNEXT_OK;
+    const int ie = in_dtype == VNEXT_BF16 ? 8 : 4;
+    VNEXT_CHECK_ARG(a && weight && bias2d && reference_points && level_wh && out && al16(a) && al16(weight) && al16(out) &&
+                        al16(reference_points) && lda % ie == 0 && K % ie == 0 && ldo % 4 == 0,
+                    "vnext_linear_msda_front: null or unaligned pointer (16-byte alignment, lda / K multiples of %d)", ie);
+    LinearArgs x{in_dtype, VNEXT_F32, a, lda, weight, nullptr, bias2d, bias_period, ldb2, nullptr, 0, nullptr, 0,
+                 nullptr, nullptr, 0.f, out, ldo, M, 384, K, 0};
+    x.msda_ref = reference_points;
+    x.msda_wh = level_wh;
+    return linear_tc_device(x, static_cast<cudaStream_t>(stream));
 }

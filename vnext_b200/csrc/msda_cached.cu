@@ -144,8 +144,12 @@ struct CachedPass {        // where this lane's sample of a pass lives
     bool live;
 };
 
-template <typename VT, int LK, bool FUSED>
+// FRONT: 0 = classic (sampling_loc / attn_weight tensors); 1 = fused (raw offsets | logits rows + reference points: location
+// arithmetic and softmax here); 2 = the same row layout, but already holding locations | normalised weights (written by the
+// projection GEMM's epilogue, vnext_linear_msda_front)
+template <typename VT, int LK, int FRONT>
 __global__ void __launch_bounds__(kCachedThreads, 1) msda_fwd_cached_kernel(const __grid_constant__ CachedParams p) {
+    constexpr bool FUSED = FRONT == 1;
     using RW = CachedRow<VT>;
     constexpr int VEC = RW::VEC, LPC = RW::LPC, NG = 32 / LPC, ROWB = RW::ROWB;
     constexpr int PPP = 32 / LK;          // (query, head) pairs per 32-sample warp pass
@@ -198,15 +202,18 @@ __global__ void __launch_bounds__(kCachedThreads, 1) msda_fwd_cached_kernel(cons
             in.a0 = in.a1 = in.a2 = 0.f;
             if constexpr (FUSED) in.r0 = in.r1 = 0.f;
             if (s.live) {
-                if constexpr (FUSED) {
+                if constexpr (FRONT != 0) {
                     const float *rowp = p.oa + (size_t)s.row * p.oa_pitch;
                     const float2 off = ldg_stream_f2(rowp + (s.m * LK + smp) * 2);
                     in.a0 = off.x; in.a1 = off.y;
                     in.a2 = ldg_stream_f1(rowp + p.n_off + s.m * LK + smp);
+                }
+                if constexpr (FUSED) {
                     // (no L1 allocation either: the reference grid is 0.6 MB per frame set and would evict corner rows)
                     const float2 rf = ldg_stream_f2(p.ref + s.n * p.ref_batch_stride + ((size_t)(s.row - s.n * p.S) * p.L + lvl) * 2);
                     in.r0 = rf.x; in.r1 = rf.y;
-                } else {
+                }
+                if constexpr (FRONT == 0) {
                     const size_t si = ((size_t)s.row * p.M + s.m) * LK + smp;
                     const float2 xy = ldg_stream_f2(p.loc + 2 * si);
                     in.a0 = xy.x; in.a1 = xy.y;
@@ -341,9 +348,9 @@ static int cached_span(int nq_axis, int n_axis, int t) {   // pixels of a level 
     return (int)(((long long)t * n_axis + nq_axis - 1) / nq_axis) + 1;
 }
 
-template <typename VT, int LK, bool FUSED>
+template <typename VT, int LK, int FRONT>
 static int launch_cached(const CachedParams &p, int grid, cudaStream_t stream) {
-    auto kern = msda_fwd_cached_kernel<VT, LK, FUSED>;
+    auto kern = msda_fwd_cached_kernel<VT, LK, FRONT>;
     static bool configured = false;
     if (!configured) {
         VNEXT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxL1));
@@ -355,12 +362,12 @@ static int launch_cached(const CachedParams &p, int grid, cudaStream_t stream) {
     return VNEXT_OK;
 }
 
-template <typename VT, bool FUSED>
+template <typename VT, int FRONT>
 static int dispatch_cached(const CachedParams &p, int LK, int grid, cudaStream_t stream) {
     switch (LK) {
-        case 8: return launch_cached<VT, 8, FUSED>(p, grid, stream);
-        case 16: return launch_cached<VT, 16, FUSED>(p, grid, stream);
-        case 32: return launch_cached<VT, 32, FUSED>(p, grid, stream);
+        case 8: return launch_cached<VT, 8, FRONT>(p, grid, stream);
+        case 16: return launch_cached<VT, 16, FRONT>(p, grid, stream);
+        case 32: return launch_cached<VT, 32, FRONT>(p, grid, stream);
         default: break;
     }
     set_error("msda cached kernel: unsupported L*K = %d", LK);
@@ -383,11 +390,15 @@ int msda_forward_cached_device(int dtype, const void *value, const int64_t *hsha
     VNEXT_CHECK_ARG((long long)N * S * M * rowb < (1ll << 32) && (long long)N * S * M * LK < (1ll << 30),
                     "msda cached kernel: tensor too large for 32-bit offsets");
     VNEXT_CHECK_ARG((reinterpret_cast<uintptr_t>(value) & 15u) == 0, "msda cached kernel: value must be 16-byte aligned");
-    const bool fused = oa != nullptr;
+    const bool fused = oa != nullptr && ref != nullptr;
+    const bool pre = oa != nullptr && ref == nullptr;        // rows already hold locations | normalised attention weights
     if (fused) {
-        VNEXT_CHECK_ARG(ref && ref_dim == 2 && oa_pitch >= M * LK * 3 && oa_pitch % 2 == 0 &&
+        VNEXT_CHECK_ARG(ref_dim == 2 && oa_pitch >= M * LK * 3 && oa_pitch % 2 == 0 &&
                             (reinterpret_cast<uintptr_t>(oa) & 7u) == 0 && (reinterpret_cast<uintptr_t>(ref) & 7u) == 0,
                         "msda cached kernel: bad fused front-end arguments (2-d reference points only: encoder self-attention)");
+    } else if (pre) {
+        VNEXT_CHECK_ARG(oa_pitch >= M * LK * 3 && oa_pitch % 2 == 0 && (reinterpret_cast<uintptr_t>(oa) & 7u) == 0,
+                        "msda cached kernel: bad pre-located front-end arguments");
     } else {
         VNEXT_CHECK_ARG(loc && attn && (reinterpret_cast<uintptr_t>(loc) & 7u) == 0, "msda cached kernel: bad loc/attn pointers");
     }
@@ -450,12 +461,13 @@ int msda_forward_cached_device(int dtype, const void *value, const int64_t *hsha
     const int grid = num_sms();
     int rc;
     if (dtype == VNEXT_F32)
-        rc = fused ? dispatch_cached<float, true>(p, LK, grid, stream) : dispatch_cached<float, false>(p, LK, grid, stream);
+        rc = fused ? dispatch_cached<float, 1>(p, LK, grid, stream)
+                   : (pre ? dispatch_cached<float, 2>(p, LK, grid, stream) : dispatch_cached<float, 0>(p, LK, grid, stream));
     else
-        rc = fused ? dispatch_cached<__nv_bfloat16, true>(p, LK, grid, stream)
-                   : dispatch_cached<__nv_bfloat16, false>(p, LK, grid, stream);
-    set_variant(dtype == VNEXT_F32 ? (fused ? "fwd_cached_fused_f32" : "fwd_cached_f32")
-                                   : (fused ? "fwd_cached_fused_bf16" : "fwd_cached_bf16"));
+        rc = fused ? dispatch_cached<__nv_bfloat16, 1>(p, LK, grid, stream)
+                   : (pre ? dispatch_cached<__nv_bfloat16, 2>(p, LK, grid, stream) : dispatch_cached<__nv_bfloat16, 0>(p, LK, grid, stream));
+    set_variant(dtype == VNEXT_F32 ? (fused ? "fwd_cached_fused_f32" : (pre ? "fwd_cached_pre_f32" : "fwd_cached_f32"))
+                                   : (fused ? "fwd_cached_fused_bf16" : (pre ? "fwd_cached_pre_bf16" : "fwd_cached_bf16")));
     return rc;
 }
 

@@ -88,3 +88,28 @@ def conv3x3(x, weight_khwc, bias, relu=True, out_dtype=None, stride=1):
             Cout, int(stride), int(relu), torch.cuda.current_stream(x.device).cuda_stream))
     _cabi.check(rc, "vnext_conv3x3_strided_tc")
     return out
+
+
+def linear_msda_front(x, weight, bias2d, reference_points, level_hw):
+    """The encoder's offsets | logits projection with the sampler front-end in the epilogue (vnext_linear_msda_front):
+    x [..., K] (fp32 or bf16, weight same dtype [384, K]); bias2d [S, 384] fp32 (row-periodic: (pos W^T + b) per pixel);
+    reference_points [S, 4, 2] fp32; level_hw = 4 x (H, W).  -> [..., 384] fp32: sampling locations | softmax weights."""
+    import ctypes
+    K = x.shape[-1]
+    x2 = _rows(x, K)
+    M = x2.shape[0]
+    assert weight.shape == (384, K) and x.dtype == weight.dtype and bias2d.shape[1] == 384 and len(level_hw) == 4
+    ref = reference_points.reshape(-1, 8)
+    assert ref.is_contiguous() and ref.shape[0] == bias2d.shape[0] and ref.dtype == torch.float32
+    out = torch.empty((M, 384), dtype=torch.float32, device=x.device)
+    wh = (ctypes.c_float * 8)(*[float(v) for hw in level_hw for v in (hw[1], hw[0])])
+    ie = x.element_size()
+    info = {"flops": 2.0 * M * 384 * K, "bytes": float(ie * (M * K + 384 * K) + 4 * M * 384 * 2)}
+    tag = "tf32" if x.dtype == torch.float32 else "bf16"
+    with torch.cuda.device(x.device):
+        rc = _cabi.timed_call(f"linear_{tag}_m{M}_n384_k{K}_msda_front", info, x, lambda: _cabi.lib().vnext_linear_msda_front(
+            _DT[x.dtype], x2.data_ptr(), x2.stride(0), weight.data_ptr(), bias2d.data_ptr(), bias2d.shape[0], bias2d.stride(0),
+            ref.data_ptr(), ctypes.cast(wh, ctypes.c_void_p), out.data_ptr(), 384, M, K,
+            torch.cuda.current_stream(x.device).cuda_stream))
+    _cabi.check(rc, "vnext_linear_msda_front")
+    return out.view(*x.shape[:-1], 384)

@@ -202,6 +202,28 @@ def ms_deform_attn_fused(value, spatial_shapes, level_start_index, offsets_logit
     return out
 
 
+def ms_deform_attn_located(value, loc_attn, n_levels, n_points, host_geom):
+    """Self-attention sampling from rows that already hold [sampling locations (M*L*P*2) | normalised weights (M*L*P)] — the
+    output of linear.linear_msda_front — through the cache-blocked kernel (no front-end arithmetic in the sampler).
+    value [N,S,M,32]; loc_attn [N,S,M*L*P*3] fp32; host_geom = (shapes, level_start_index) host int64 arrays."""
+    N, S, M, D = value.shape
+    L, P = n_levels, n_points
+    _require(value.is_cuda and value.is_contiguous() and loc_attn.stride(-1) == 1 and loc_attn.dtype == torch.float32 and
+             loc_attn.shape[1] == S and D == 32 and value.dtype in WINDOW_MARGIN, "ms_deform_attn_located: bad arguments")
+    hs, hl = host_geom
+    _require(_pyramid_in_order(hs, hl, S), "ms_deform_attn_located: levels must tile [0, S) in order")
+    la = loc_attn.reshape(N * S, loc_attn.shape[-1])
+    out = torch.empty((N, S, M * D), dtype=value.dtype, device=value.device)
+    e = value.element_size()
+    info = {"bytes": float(N) * (e * S * M * D + 4 * 3 * S * M * L * P + e * S * M * D), "N": N, "Lq": S, "S": S}
+    with torch.cuda.device(value.device):
+        rc = _cabi.timed_call("msda_cached_located_enc", info, value, lambda: _cabi.lib().vnext_msda_forward_selfattn(
+            _DTYPES[value.dtype], value.data_ptr(), hs.ctypes.data, hl.ctypes.data, None, None, la.data_ptr(), la.stride(0),
+            None, 0, 0, N, S, M, D, L, P, -1, out.data_ptr(), _stream(value)))
+    _cabi.check(rc, "ms_deform_attn_located")
+    return out
+
+
 def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
                             im2col_step):
     N, S, M, D, L, Lq, P = _check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,

@@ -113,6 +113,7 @@ class SeqFormerEngine:
         self.act_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
         import os
         self._small_fp32 = os.environ.get("VNEXT_SMALL_FP32", "0") == "1"
+        self._front_in_gemm = os.environ.get("VNEXT_MSDA_FRONT_GEMM", "1") == "1"
         self._two_stream_decoder = os.environ.get("VNEXT_TWO_STREAM_DECODER", "1") == "1"
         parts = os.environ.get("VNEXT_BF16_PARTS", "backbone,encoder").split(",")     # experiment switch (tools/bf16_error_budget.py)
         self.bb_dtype = self.act_dtype if "backbone" in parts else torch.float32      # backbone + input projection storage
@@ -498,11 +499,20 @@ class SeqFormerEngine:
     def encoder(self, x, plan):
         for i, w in enumerate(self.enc):
             a = w["attn"]
-            if self.native_gemm:
-                oa = self.lin(x, (a["oa_w"], None), bias2d=plan.extra["enc_posproj"][i], out_dtype=torch.float32)
+            from .. import msda
+            if (self.native_gemm and self._front_in_gemm and (self.M, self.L, self.P) == (8, 4, 4) and
+                    msda.WINDOW_MODE == "cached"):
+                # softmax + location arithmetic in the projection's epilogue; the sampler reads locations | weights
+                from ..linear import linear_msda_front
+                la = linear_msda_front(x, self._w(a["oa_w"], x.dtype), plan.extra["enc_posproj"][i], plan.enc_ref[0],
+                                       plan.level_hw)
+                s = msda.ms_deform_attn_located(self._value(x, a, plan), la, self.L, self.P, plan.extra["host_geom"])
             else:
-                oa = F.linear(x + plan.pos_flat, a["oa_w"], a["oa_b"])
-            s = self.sample(self._value(x, a, plan), oa, plan.enc_ref, plan, a["n_off"])
+                if self.native_gemm:
+                    oa = self.lin(x, (a["oa_w"], None), bias2d=plan.extra["enc_posproj"][i], out_dtype=torch.float32)
+                else:
+                    oa = F.linear(x + plan.pos_flat, a["oa_w"], a["oa_b"])
+                s = self.sample(self._value(x, a, plan), oa, plan.enc_ref, plan, a["n_off"])
             if self.native_gemm:     # branch tensors in act_dtype (bf16 in bf16 mode), residual stream x in fp32
                 x = self.lin(s, (a["o_w"], a["o_b"]), residual=x, ln=w["norm1"], out_dtype=torch.float32)
                 h = self.lin(x, w["lin1"], relu=True, out_dtype=self.hid_dtype)
