@@ -181,6 +181,20 @@ int vnext_linear_tc(int in_dtype, int out_dtype, const void *a, int lda, const v
                     int ldo, int M, int N, int K, int flags, void *stream);
 
 /*
+ * COCO run-length encoding of boolean masks on the device (csrc/rle_encode.cu) — what the reference's evaluator computes on
+ * the host for every predicted mask right after the hot path: `mask_util.encode(np.array(mask[:, :, None], order="F"))[0]`
+ * (projects/IDOL/idol/data/ytvis_eval.py:174-214, projects/SeqFormer/seqformer/data/ytvis_eval.py:171-211; pycocotools
+ * maskApi.c rleEncode + rleToString).  masks [n_masks, H, W] bytes (row-major, 0 / non-zero); the strings of all masks are
+ * written back to back into chars (device), char_offsets [n_masks + 1] int64 (device): mask i's "counts" string is
+ * chars[char_offsets[i] : char_offsets[i + 1]].  char_offsets[n_masks] is the total even when it exceeds chars_capacity (then
+ * only the first chars_capacity bytes were written: call again with a larger buffer).  workspace: device memory, 256-byte
+ * aligned, at least vnext_rle_workspace_bytes(n_masks, H, W) bytes.  Six launches of fixed grid size (graph capturable).
+ */
+long long vnext_rle_workspace_bytes(int n_masks, int H, int W);
+int vnext_rle_encode(const unsigned char *masks, int n_masks, int H, int W, void *workspace, long long workspace_bytes,
+                     long long *char_offsets, unsigned char *chars, long long chars_capacity, void *stream);
+
+/*
  * The encoder's offsets | logits projection with the sampler's front-end fused into the epilogue (N = 384 = 8 heads x (4 levels
  * x 4 points x 2 | 4 x 4)): out[row, 0:256] = reference_points[row % period, level, xy] + (a W^T + bias2d)[.] / (W_level | H_level),
  * out[row, 256:384] = softmax over each head's 16 logits — MSDeformAttn.forward between its two Linears and the sampling op

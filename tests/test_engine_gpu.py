@@ -177,3 +177,23 @@ def test_clip_matching_inference_long_video():
 def test_clip_tracker_on_device_matches_reference(name):
     from test_seqformer_clipmatch_golden import run_case
     run_case(name, "cuda")
+
+
+def test_adjacent_pinned_uint8_frames_are_copied_straight_from_the_callers_memory():
+    """A clip held as one pinned uint8 buffer: one H2D copy from it (no staging copy); same result as separate float frames."""
+    from vnext_b200.seqformer.meta_arch import SeqFormer
+    T, H, W, seed = 3, 96, 128, 0
+    sd = fill_state_dict(seqformer_r50_state_spec(), seed)
+    frames = synthetic_clip(T, H, W, seed)
+    block = torch.stack(frames).to(torch.uint8).pin_memory()
+    model = SeqFormer(state_dict=sd, device="cuda", precision="fp32").eval()
+    run = model.runner(T, H, W, (H, W))
+    views = [f for f in block]
+    assert run._pinned_block(views) is not None and run._pinned_block(views).data_ptr() == block.data_ptr()
+    assert run._pinned_block([f.clone() for f in block]) is None                  # separate allocations
+    assert run._pinned_block(views[::-1]) is None                                  # not in order
+    assert run._pinned_block([f.float() for f in block]) is None
+    want = model([{"image": frames, "height": H, "width": W}])
+    got = model([{"image": views, "height": H, "width": W}])
+    assert got["pred_scores"] == want["pred_scores"] and got["pred_labels"] == want["pred_labels"]
+    assert all(torch.equal(a, b) for a, b in zip(got["pred_masks"], want["pred_masks"]))

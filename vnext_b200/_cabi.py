@@ -30,6 +30,9 @@ SIGNATURES = {
     "vnext_linear_tc": (_c_int, [_c_int, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p,
                                  _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, ctypes.c_float, _c_void_p, _c_int,
                                  _c_int, _c_int, _c_int, _c_int, _c_void_p]),
+    "vnext_rle_workspace_bytes": (ctypes.c_longlong, [_c_int, _c_int, _c_int]),
+    "vnext_rle_encode": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_void_p, ctypes.c_longlong, _c_void_p, _c_void_p,
+                                  ctypes.c_longlong, _c_void_p]),
     "vnext_linear_msda_front": (_c_int, [_c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p,
                                          _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
     "vnext_conv3x3_tc": (_c_int, [_c_int, _c_int] + [_c_void_p] * 4 + [_c_int] * 6 + [_c_void_p]),

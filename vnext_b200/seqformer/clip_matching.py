@@ -112,8 +112,9 @@ class ClipTracks:
 
 @torch.no_grad()
 def clip_matching_postprocess(pred_cls, pred_masks, ori_size, image_size, mask_stride=4, multi_cls=True,
-                              apply_cls_thres=0.05):
-    """seqformer.py:336-361: class thresholding, x4 bilinear + sigmoid, crop, nearest resize, > 0.5, to the host."""
+                              apply_cls_thres=0.05, mask_format="bool"):
+    """seqformer.py:336-361: class thresholding, x4 bilinear + sigmoid, crop, nearest resize, > 0.5, to the host (as boolean
+    tensors, or with mask_format="rle" as per-frame COCO RLE dicts encoded on the device: vnext_b200/rle.py)."""
     if len(pred_cls) == 0:
         return {"image_size": ori_size, "pred_scores": [], "pred_labels": [], "pred_masks": []}
     if multi_cls:
@@ -126,8 +127,13 @@ def clip_matching_postprocess(pred_cls, pred_masks, ori_size, image_size, mask_s
     m = F.interpolate(pred_masks, size=(h * mask_stride, w * mask_stride), mode="bilinear", align_corners=False).sigmoid()
     m = m[:, :, :image_size[0], :image_size[1]]
     m = F.interpolate(m, size=(ori_size[0], ori_size[1]), mode="nearest") > 0.5
-    return {"image_size": ori_size, "pred_scores": scores.tolist(), "pred_labels": labels.tolist(),
-            "pred_masks": [x for x in m.cpu()]}
+    if mask_format == "rle":
+        from ..rle import encode
+        flat, t = encode(m), m.shape[1]
+        masks = [flat[i * t:(i + 1) * t] for i in range(m.shape[0])]
+    else:
+        masks = [x for x in m.cpu()]
+    return {"image_size": ori_size, "pred_scores": scores.tolist(), "pred_labels": labels.tolist(), "pred_masks": masks}
 
 
 def clip_windows(video_length, clip_length, clip_stride):

@@ -886,7 +886,8 @@ class SeqFormerEngine:
     @staticmethod
     def finish_video(valid_scores, masks, ori_size, apply_cls_thres=0.05, multi_cls=True):
         """Host part of whole_video_inference (seqformer.py:383-409): thresholding and list building."""
-        valid_scores, masks = valid_scores.cpu(), masks.cpu()
+        valid_scores = valid_scores.cpu()
+        masks = masks if isinstance(masks, list) else masks.cpu()     # list: per instance, per frame RLE dicts (mask_format="rle")
         if multi_cls:
             above = torch.where(valid_scores > apply_cls_thres)
             scores, labels = valid_scores[above], above[1]

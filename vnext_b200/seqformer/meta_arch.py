@@ -33,6 +33,9 @@ class SeqFormer(nn.Module):
         self.pixel_std = tuple(g("MODEL.PIXEL_STD", (58.395, 57.120, 57.375)))
         self.device_name = g("MODEL.DEVICE", device)
         self.precision = precision
+        # "bool": pred_masks = boolean [T, H, W] tensors like the reference; "rle": pred_masks = per frame COCO RLE dicts, encoded on
+        # the device — what ytvis_eval.instances_to_coco_json_video makes of them next (see vnext_b200/seqformer/ytvis_eval.py)
+        self.mask_format = "bool"
         # backbone: build_resnet_backbone (R50) or D2SwinTransformer (cfg.MODEL.SWIN.*, S/config.py:67-83)
         self.swin = None
         if g("MODEL.BACKBONE.NAME", "build_resnet_backbone") == "D2SwinTransformer":
@@ -70,9 +73,9 @@ class SeqFormer(nn.Module):
         self._runners = {}
 
     def runner(self, T, H, W, ori_size, slot=0):
-        key = (T, H, W, tuple(ori_size), slot)
+        key = (T, H, W, tuple(ori_size), slot, self.mask_format)
         if key not in self._runners:
-            self._runners[key] = ClipRunner(self.engine, T, H, W, ori_size)
+            self._runners[key] = ClipRunner(self.engine, T, H, W, ori_size, mask_format=self.mask_format)
         return self._runners[key]
 
     def stream(self, videos, depth=2):
@@ -98,7 +101,7 @@ class SeqFormer(nn.Module):
             ori = (video.get("height", H), video.get("width", W))
             if len(pending) == depth:
                 yield finish()
-            if (len(frames), H, W, tuple(ori), n % depth) not in self._runners:
+            if (len(frames), H, W, tuple(ori), n % depth, self.mask_format) not in self._runners:
                 # a runner's construction (eager warm-up + graph capture) never overlaps a clip in flight: drain first,
                 # then build every slot of this geometry at once
                 while pending:
@@ -188,7 +191,7 @@ def _clip_matching_forward(self, frames, ori):
         tracks.update(frame_idx, cls, logits)
     pred_cls, pred_logits = tracks.get_result()
     return clip_matching_postprocess(pred_cls, pred_logits, ori, (H, W), self.mask_stride, self.is_multi_cls,
-                                     self.apply_cls_thres)
+                                     self.apply_cls_thres, mask_format=self.mask_format)
 
 
 SeqFormer._forward_clip_matching = _clip_matching_forward
