@@ -67,7 +67,10 @@ def resnet50(sd, x, prefix=BB):
     out = {}
     x = _conv_bn(sd, prefix + "stem.conv1", x, stride=2, padding=3)
     x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
-    for stage, nblocks in (("res2", 3), ("res3", 4), ("res4", 6), ("res5", 3)):
+    for stage in ("res2", "res3", "res4", "res5"):            # block count per stage read off the keys (R50 3,4,6,3; R101 3,4,23,3)
+        nblocks = 0
+        while f"{prefix}{stage}.{nblocks}.conv1.weight" in sd:
+            nblocks += 1
         for b in range(nblocks):
             p = f"{prefix}{stage}.{b}."
             stride = 2 if (b == 0 and stage != "res2") else 1

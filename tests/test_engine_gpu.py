@@ -197,3 +197,17 @@ def test_adjacent_pinned_uint8_frames_are_copied_straight_from_the_callers_memor
     got = model([{"image": views, "height": H, "width": W}])
     assert got["pred_scores"] == want["pred_scores"] and got["pred_labels"] == want["pred_labels"]
     assert all(torch.equal(a, b) for a, b in zip(got["pred_masks"], want["pred_masks"]))
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("tf32", 1e-2)])
+def test_resnet101_backbone_engine_vs_oracle(precision, tol):
+    """cfg.MODEL.RESNETS.DEPTH: 101 (projects/IDOL/configs/ytvis19_r101.yaml): 23 res4 blocks found from the checkpoint keys."""
+    from vnext_b200.seqformer.engine import SeqFormerEngine
+    T, H, W, seed = 2, 96, 128, 3
+    sd = fill_state_dict(seqformer_r50_state_spec(depth=101), seed)
+    frames = synthetic_clip(T, H, W, seed)
+    out = SeqFormerEngine(sd, device="cuda", precision=precision).inference(torch.stack(frames).cuda())
+    with torch.no_grad():
+        ref = SO.inference(sd, frames)
+    for k in ("pred_logits", "pred_boxes", "pred_masks"):
+        assert _rel(out[k].float().cpu(), ref[k]) < tol, k

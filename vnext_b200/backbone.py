@@ -95,8 +95,9 @@ def _get(cfg, path, default):
 
 def build_resnet_backbone(cfg=None, input_shape=None, **kw):
     depth = _get(cfg, "MODEL.RESNETS.DEPTH", 50)
-    if depth != 50 or _get(cfg, "MODEL.RESNETS.STRIDE_IN_1X1", False):
-        raise NotImplementedError("vnext_b200 builds the reference's ResNet-50, STRIDE_IN_1X1: False (configs/base_ytvis.yaml)")
+    if depth not in (50, 101, 152) or _get(cfg, "MODEL.RESNETS.STRIDE_IN_1X1", False):
+        raise NotImplementedError("vnext_b200 builds the reference's bottleneck ResNets (depth 50 / 101 / 152), STRIDE_IN_1X1: "
+                                  "False (configs/base_ytvis.yaml)")
     return B200Backbone("resnet50", out_features=_get(cfg, "MODEL.RESNETS.OUT_FEATURES", ("res2", "res3", "res4", "res5")), **kw)
 
 

@@ -44,6 +44,7 @@ class IDOL(nn.Module):
                                                g("MODEL.IDOL.DEC_LAYERS", 6), g("MODEL.IDOL.DEEP_SUPERVISION", True))
         # backbone: build_resnet_backbone (R50) or D2SwinTransformer (cfg.MODEL.SWIN.*, I/config.py, configs/*swinL.yaml)
         self.swin = None
+        self.resnet_depth = g("MODEL.RESNETS.DEPTH", 50)          # 50 / 101 (configs/ytvis19_r101.yaml) / 152
         if "swin" in str(g("MODEL.BACKBONE.NAME", "build_resnet_backbone")).lower():
             self.swin = dict(embed_dim=g("MODEL.SWIN.EMBED_DIM", 96), depths=tuple(g("MODEL.SWIN.DEPTHS", (2, 2, 6, 2))),
                              num_heads=tuple(g("MODEL.SWIN.NUM_HEADS", (3, 6, 12, 24))),
@@ -58,7 +59,7 @@ class IDOL(nn.Module):
         self._state_dict = state_dict
         if not keep_train_model:
             self._train_model = None
-        spec = idol_r50_state_spec(self.num_queries, self.num_classes, swin=self.swin)
+        spec = idol_r50_state_spec(self.num_queries, self.num_classes, swin=self.swin, depth=self.resnet_depth)
         missing = [k for k in spec if k not in state_dict]
         if missing:
             raise KeyError(f"checkpoint is missing {len(missing)} keys, e.g. {missing[:3]}")

@@ -3,9 +3,9 @@ module tree of `IDOL` (projects/IDOL/idol/idol.py:77-203) = CondInst_segm(Deform
 from ..seqformer.state_spec import _linear, _ln, _mha, _msda, resnet50_spec
 
 
-def idol_r50_state_spec(num_queries=300, num_classes=40, C=256, ffn=1024, M=8, L=4, P=4, enc=6, dec=6, swin=None):
+def idol_r50_state_spec(num_queries=300, num_classes=40, C=256, ffn=1024, M=8, L=4, P=4, enc=6, dec=6, swin=None, depth=50):
     if swin is None:
-        spec = resnet50_spec("detr.detr.backbone.0.backbone.")
+        spec = resnet50_spec("detr.detr.backbone.0.backbone.", depth)
         in_ch = (512, 1024, 2048)
     else:
         from ..swin_spec import swin_state_spec

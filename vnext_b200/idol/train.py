@@ -147,7 +147,8 @@ class IDOLTrainModel(nn.Module):
         if self.tc:                                   # weight-gradient GEMMs (cuBLAS) in TF32 as well; process-global flag
             torch.backends.cuda.matmul.allow_tf32 = True
         self.device = torch.device(device)
-        spec = self._state_spec(num_queries, num_classes)
+        from ..seqformer.state_spec import resnet_depth_of
+        spec = self._state_spec(num_queries, num_classes, resnet_depth_of(state_dict))
         missing = [k for k in spec if k not in state_dict]
         if missing:
             raise KeyError(f"checkpoint is missing {len(missing)} keys, e.g. {missing[:3]}")
@@ -176,8 +177,8 @@ class IDOLTrainModel(nn.Module):
         self.dec_layers = 1 + max(int(k.split(".")[5]) for k in spec if k.startswith(TR + "decoder.layers."))
 
     @staticmethod
-    def _state_spec(num_queries, num_classes):
-        return idol_r50_state_spec(num_queries, num_classes)
+    def _state_spec(num_queries, num_classes, depth=50):
+        return idol_r50_state_spec(num_queries, num_classes, depth=depth)
 
     # ------------------------------------------------------------------ state dict in the reference's layout
     def reference_state_dict(self):
@@ -226,7 +227,10 @@ class IDOLTrainModel(nn.Module):
         with torch.no_grad():
             x = self._conv_bn(BB + "stem.conv1", x, stride=2, padding=3)
             x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
-        for stage, nblocks in (("res2", 3), ("res3", 4), ("res4", 6), ("res5", 3)):
+        for stage in ("res2", "res3", "res4", "res5"):       # block counts from the checkpoint's keys (R50 / R101 / R152)
+            nblocks = 0
+            while f"{BB}{stage}.{nblocks}.conv1.weight" in self.P:
+                nblocks += 1
             for b in range(nblocks):
                 p = f"{BB}{stage}.{b}."
                 stride = 2 if (b == 0 and stage != "res2") else 1

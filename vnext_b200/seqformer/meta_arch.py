@@ -38,6 +38,7 @@ class SeqFormer(nn.Module):
         self.mask_format = "bool"
         # backbone: build_resnet_backbone (R50) or D2SwinTransformer (cfg.MODEL.SWIN.*, S/config.py:67-83)
         self.swin = None
+        self.resnet_depth = g("MODEL.RESNETS.DEPTH", 50)          # 50 / 101 (configs/*_r101.yaml) / 152
         if g("MODEL.BACKBONE.NAME", "build_resnet_backbone") == "D2SwinTransformer":
             self.swin = dict(embed_dim=g("MODEL.SWIN.EMBED_DIM", 96), depths=tuple(g("MODEL.SWIN.DEPTHS", (2, 2, 6, 2))),
                              num_heads=tuple(g("MODEL.SWIN.NUM_HEADS", (3, 6, 12, 24))),
@@ -53,7 +54,7 @@ class SeqFormer(nn.Module):
             self.load_reference_state_dict(state_dict)
 
     def expected_state_spec(self):
-        return seqformer_r50_state_spec(self.num_queries, self.num_classes, swin=self.swin)
+        return seqformer_r50_state_spec(self.num_queries, self.num_classes, swin=self.swin, depth=self.resnet_depth)
 
     def load_reference_state_dict(self, state_dict):
         """Takes a reference-layout checkpoint (`model` dict of a DetectionCheckpointer .pth)."""

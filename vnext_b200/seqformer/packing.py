@@ -13,7 +13,20 @@ folded products), done once when a checkpoint is loaded, invisible to the checkp
 import torch
 
 BB = "detr.detr.backbone.0.backbone."
-R50_STAGES = (("res2", 3), ("res3", 4), ("res4", 6), ("res5", 3))
+STAGE_NAMES = ("res2", "res3", "res4", "res5")
+
+
+def resnet_blocks(sd, prefix=BB):
+    """(stage, number of bottleneck blocks) read off the checkpoint's keys: ResNet-50 (3,4,6,3), -101 (3,4,23,3), ..."""
+    out = []
+    for stage in STAGE_NAMES:
+        n = 0
+        while f"{prefix}{stage}.{n}.conv1.weight" in sd:
+            n += 1
+        if n == 0:
+            raise KeyError(f"checkpoint has no {prefix}{stage}.0.conv1.weight")
+        out.append((stage, n))
+    return tuple(out)
 
 
 def fold_conv_bn(sd, prefix, eps=1e-5):
@@ -27,7 +40,7 @@ def fold_conv_bn(sd, prefix, eps=1e-5):
 def pack_resnet50(sd, prefix=BB):
     """-> list of stages; each block = dict(conv1=(w,b), conv2=(w,b,stride), conv3=(w,b), shortcut=(w,b,stride)|None)."""
     packed = {"stem": fold_conv_bn(sd, prefix + "stem.conv1"), "stages": []}
-    for stage, nblocks in R50_STAGES:
+    for stage, nblocks in resnet_blocks(sd, prefix):
         blocks = []
         for b in range(nblocks):
             p = f"{prefix}{stage}.{b}."

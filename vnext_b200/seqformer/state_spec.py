@@ -11,6 +11,25 @@ Used to synthesise weights offline and to validate a loaded checkpoint before pa
 """
 
 R50_STAGES = (("res2", 3, 64, 256), ("res3", 4, 128, 512), ("res4", 6, 256, 1024), ("res5", 3, 512, 2048))
+# bottleneck ResNets of detectron2/modeling/backbone/resnet.py:656-662 (`num_blocks_per_stage`); channels are the same
+BLOCKS_PER_STAGE = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3), 152: (3, 8, 36, 3)}
+
+
+def resnet_stages(depth=50):
+    if depth not in BLOCKS_PER_STAGE:
+        raise NotImplementedError(f"ResNet depth {depth}: the bottleneck depths 50 / 101 / 152 are built "
+                                  "(projects/IDOL/configs/ytvis19_r50.yaml, ytvis19_r101.yaml)")
+    return tuple((name, n, mid, cout) for (name, _, mid, cout), n in zip(R50_STAGES, BLOCKS_PER_STAGE[depth]))
+
+
+def resnet_depth_of(state_dict, prefix="detr.detr.backbone.0.backbone."):
+    """The bottleneck ResNet depth a checkpoint holds, from its res3 / res4 block counts (50 when it has no ResNet keys)."""
+    n3 = sum(1 for k in state_dict if k.startswith(prefix + "res3.") and k.endswith(".conv1.weight"))
+    n4 = sum(1 for k in state_dict if k.startswith(prefix + "res4.") and k.endswith(".conv1.weight"))
+    for depth, blocks in BLOCKS_PER_STAGE.items():
+        if (n3, n4) == blocks[1:3]:
+            return depth
+    return 50
 
 
 def _conv_bn(spec, p, cout, cin, k):
@@ -19,11 +38,11 @@ def _conv_bn(spec, p, cout, cin, k):
         spec[f"{p}.norm.{n}"] = (cout,)
 
 
-def resnet50_spec(prefix):
+def resnet50_spec(prefix, depth=50):
     spec = {}
     _conv_bn(spec, prefix + "stem.conv1", 64, 3, 7)
     cin = 64
-    for stage, nblocks, mid, cout in R50_STAGES:
+    for stage, nblocks, mid, cout in resnet_stages(depth):
         for b in range(nblocks):
             p = f"{prefix}{stage}.{b}."
             if cin != cout:
@@ -60,10 +79,11 @@ def _mha(spec, p, C):
     _linear(spec, p + ".out_proj", C, C)
 
 
-def seqformer_r50_state_spec(num_queries=300, num_classes=40, C=256, ffn=1024, M=8, L=4, P=4, enc=6, dec=6, swin=None):
-    """swin: None for ResNet-50, else a Swin cfg dict (vnext_b200.swin_spec.SWIN_L ...)."""
+def seqformer_r50_state_spec(num_queries=300, num_classes=40, C=256, ffn=1024, M=8, L=4, P=4, enc=6, dec=6, swin=None,
+                             depth=50):
+    """swin: None for a ResNet (depth 50 / 101 / 152: cfg.MODEL.RESNETS.DEPTH), else a Swin cfg dict (swin_spec.SWIN_L ...)."""
     if swin is None:
-        spec = resnet50_spec("detr.detr.backbone.0.backbone.")
+        spec = resnet50_spec("detr.detr.backbone.0.backbone.", depth)
         in_ch = (512, 1024, 2048)
     else:
         from ..swin_spec import swin_state_spec

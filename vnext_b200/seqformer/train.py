@@ -28,8 +28,8 @@ class SeqFormerTrainModel(IDOLTrainModel):
         self.criterion = crit.SetCriterion(self.num_classes, self.weight_dict, num_frames, mask_out_stride=self.mask_stride)
 
     @staticmethod
-    def _state_spec(num_queries, num_classes):
-        return seqformer_r50_state_spec(num_queries, num_classes)
+    def _state_spec(num_queries, num_classes, depth=50):
+        return seqformer_r50_state_spec(num_queries, num_classes, depth=depth)
 
     # ------------------------------------------------------------------ decode-mode MSDeformAttn (ms_deform_attn.py:128-217)
     def _sample(self, p, query_box, ref, value, shapes, lsi):
