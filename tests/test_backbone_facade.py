@@ -22,8 +22,9 @@ def test_interface_matches_detectron2_backbone():
         {"res3": 384, "res4": 768, "res5": 1536}
     with pytest.raises(RuntimeError, match="no weights loaded"):
         r(torch.zeros(1, 3, 32, 32))
+    assert build_resnet_backbone({"MODEL": {"RESNETS": {"DEPTH": 101}}}).kind == "resnet50"      # bottleneck family: 50 / 101 / 152
     with pytest.raises(NotImplementedError):
-        build_resnet_backbone({"MODEL": {"RESNETS": {"DEPTH": 101}}})
+        build_resnet_backbone({"MODEL": {"RESNETS": {"DEPTH": 34}}})
 
 
 @pytest.mark.gpu
