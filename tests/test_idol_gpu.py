@@ -55,6 +55,20 @@ def test_idol_facade_chunks_long_videos():
     assert len(res["pred_scores"]) == len(res["pred_labels"]) == len(res["pred_masks"])
     for per_frame in res["pred_masks"]:
         assert len(per_frame) == 5 and all(x is None or tuple(x.shape) == (72, 100) for x in per_frame)
+    # the same video with the masks in the evaluator's wire format (device RLE): every string decodes to the boolean mask
+    from oracle import rle_oracle as R
+    m.mask_format = "rle"
+    rle = m([{"image": frames, "height": 72, "width": 100}])
+    m.mask_format = "bool"
+    assert rle["pred_scores"] == res["pred_scores"] and rle["pred_labels"] == res["pred_labels"]
+    n_masks = 0
+    for a, b in zip(rle["pred_masks"], res["pred_masks"]):
+        for ra, mb in zip(a, b):
+            assert (ra is None) == (mb is None)
+            if ra is not None:
+                assert ra["size"] == [72, 100] and (R.decode(R.from_string(ra["counts"]), 72, 100) == mb.numpy()).all()
+                n_masks += 1
+    assert n_masks > 0 or len(res["pred_masks"]) == 0
     seen = []
     m.tracker_fn = lambda out, ori, img: seen.append((ori, img, out["pred_logits"].shape)) or "mine"
     assert m([{"image": frames, "height": 72, "width": 100}]) == "mine" and seen == [((72, 100), (96, 128), (5, 300, 40))]

@@ -43,6 +43,7 @@ class IDOL(nn.Module):
                                                g("MODEL.IDOL.MASK_WEIGHT", 2.0), g("MODEL.IDOL.DICE_WEIGHT", 5.0),
                                                g("MODEL.IDOL.DEC_LAYERS", 6), g("MODEL.IDOL.DEEP_SUPERVISION", True))
         # backbone: build_resnet_backbone (R50) or D2SwinTransformer (cfg.MODEL.SWIN.*, I/config.py, configs/*swinL.yaml)
+        self.mask_format = "bool"         # "rle": pred_masks as per-frame COCO RLE dicts, encoded on the device (vnext_b200/rle.py)
         self.swin = None
         self.resnet_depth = g("MODEL.RESNETS.DEPTH", 50)          # 50 / 101 (configs/ytvis19_r101.yaml) / 152
         if "swin" in str(g("MODEL.BACKBONE.NAME", "build_resnet_backbone")).lower():
@@ -146,7 +147,8 @@ class IDOL(nn.Module):
                               temporal_weight=self.inference_tw, memory_len=self.memory_len)        # idol.py:276-290
         return video_inference(output, tracker, ori_size, image_size, select_thres=self.inference_select_thres,
                                temporal_score_type=self.temporal_score_type, multi_cls=self.is_multi_cls,
-                               apply_cls_thres=self.apply_cls_thres, mask_stride=self.mask_stride)
+                               apply_cls_thres=self.apply_cls_thres, mask_stride=self.mask_stride,
+                               mask_format=self.mask_format)
 
 
 def register_with_detectron2():

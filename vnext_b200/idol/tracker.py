@@ -179,11 +179,12 @@ class IDOLTracker:
 
 @torch.no_grad()
 def video_inference(outputs, tracker, ori_size, image_size, select_thres=0.1, temporal_score_type="mean",
-                    multi_cls=True, apply_cls_thres=0.05, mask_stride=4):
+                    multi_cls=True, apply_cls_thres=0.05, mask_stride=4, mask_format="bool"):
     """`IDOL.inference(outputs, tracker, ori_size, image_sizes)` (idol.py:326-473).  outputs: the dense per-frame
     predictions (pred_logits [T,nq,K], pred_boxes [T,nq,4], pred_inst_embed [T,nq,C], pred_masks [T,nq,1,h,w]) on any
     device.  -> {"image_size", "pred_scores", "pred_labels", "pred_masks": per instance a list over frames of bool
-    [H,W] CPU tensors or None}."""
+    [H,W] CPU tensors or None}.  mask_format="rle" (CUDA outputs only): the frames' masks as COCO RLE dicts instead, encoded
+    on the device (vnext_b200/rle.py) — what ytvis_eval.py:196-204 makes of them next; None frames stay None."""
     logits, boxes = outputs["pred_logits"], outputs["pred_boxes"]
     embeds, masks = outputs["pred_inst_embed"], outputs["pred_masks"]
     T, nq = logits.shape[:2]
@@ -228,7 +229,12 @@ def video_inference(outputs, tracker, ori_size, image_size, select_thres=0.1, te
         qq = torch.tensor([p[2] for p in pairs], device=masks.device)
         m = F.interpolate(masks[tt, qq], size=(h * mask_stride, w * mask_stride), mode="bilinear", align_corners=False)
         m = m.sigmoid()[:, :, :image_size[0], :image_size[1]]
-        m = (F.interpolate(m, size=(ori_size[0], ori_size[1]), mode="nearest") > 0.5)[:, 0].cpu()   # ONE copy
+        m = (F.interpolate(m, size=(ori_size[0], ori_size[1]), mode="nearest") > 0.5)[:, 0]
+        if mask_format == "rle":
+            from ..rle import encode
+            m = encode(m.contiguous())                    # strings instead of H*W bytes per mask
+        else:
+            m = m.cpu()                                   # ONE copy
         for k, (i, t, _) in enumerate(pairs):
             per_inst[i][t] = m[k]
     cls = []
