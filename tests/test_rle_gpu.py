@@ -74,6 +74,14 @@ def test_uint8_masks_with_values_other_than_one():
     m = (torch.rand((2, 40, 50), generator=g) < 0.4)
     u8 = m.to(torch.uint8) * torch.randint(1, 255, m.shape, generator=g, dtype=torch.uint8)
     assert rle.encode(u8.cuda()) == rle.encode(m.cuda())
+    # a base address that is not 4-byte aligned (W % 4 == 0 otherwise takes the 4-columns-per-thread path)
+    m4 = torch.rand((3, 40, 48), generator=g) < 0.4
+    buf = torch.zeros(m4.numel() + 8, dtype=torch.uint8, device="cuda")
+    for shift in (0, 1, 2, 3):
+        view = buf[shift:shift + m4.numel()].view(3, 40, 48)
+        view.copy_(m4.to(torch.uint8))
+        got = rle.encode(view)
+        assert [g_["counts"].encode() for g_ in got] == [R.encode(x.numpy())["counts"] for x in m4]
 
 
 def test_checkerboard_overflows_the_default_buffer_and_reports_the_needed_size():

@@ -3,7 +3,8 @@
 // `mask_util.encode(np.array(mask[:, :, None], order="F"))`, i.e. pycocotools maskApi.c rleEncode + rleToString).
 //
 // A mask [H, W] (row-major bytes, 0 / non-zero) is read as the COLUMN-major pixel stream i = x*H + y.  Six small launches,
-// all of fixed grid size (CUDA-graph friendly), all integer work bound by the 1-byte mask reads:
+// all of fixed grid size (CUDA-graph friendly), all integer work bound by the mask reads (a thread walks 4 adjacent columns
+// with one 4-byte load per row when W % 4 == 0; rows are coalesced across the warp):
 //   1 count     unit = (column x, one of RLE_SEG row segments): #positions where the stream changes value
 //   2 scan      per mask, exclusive scan of the unit counts (unit order x*RLE_SEG + seg == stream order) -> n_runs
 //   3 emit      every unit writes the stream positions of its changes: positions[mask][0 .. n_runs)
@@ -20,8 +21,8 @@ using namespace vnext;
 
 namespace {
 
-constexpr int RLE_SEG = 8;            // row segments per column
-constexpr int RLE_COLS = 128;         // columns (threads) per CTA of the count / emit kernels
+constexpr int RLE_SEG = 16;           // row segments per column
+constexpr int RLE_COLS = 64;          // threads per CTA of the count / emit kernels (each owns 1 or 4 adjacent columns)
 constexpr int RLE_CHUNK = 2048;       // counts per CTA of the string kernels (256 threads x 8)
 constexpr int RLE_PER_THREAD = RLE_CHUNK / 256;
 
@@ -78,39 +79,68 @@ __device__ __forceinline__ T block_exclusive_scan(T v, T *scratch, T &total) {
     return res;
 }
 
-struct RleUnit {
-    int x, y0, y1;
-    bool prev;
+// A thread owns VEC adjacent columns (one 4-byte load per row when VEC == 4) of one row segment: VEC units.
+template <int VEC>
+struct RleUnits {
+    int x, y0, y1;          // first column, row range
+    bool prev[VEC];         // stream value just before each column's first pixel of the segment (0 before the very first pixel)
 };
 
-// The unit of this thread and the stream value just before its first pixel (0 before the very first pixel).
-__device__ __forceinline__ bool rle_unit(const unsigned char *mask, int H, int W, RleUnit &u) {
-    u.x = blockIdx.x * RLE_COLS + threadIdx.x;
+template <int VEC>
+__device__ __forceinline__ void rle_load_row(const unsigned char *row, int x, int W, bool (&v)[VEC]) {
+    if constexpr (VEC == 4) {
+        const uchar4 q = *reinterpret_cast<const uchar4 *>(row + x);          // W % 4 == 0: aligned, all four columns exist
+        v[0] = q.x != 0; v[1] = q.y != 0; v[2] = q.z != 0; v[3] = q.w != 0;
+    } else {
+        v[0] = row[x] != 0;
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ bool rle_units(const unsigned char *mask, int H, int W, RleUnits<VEC> &u) {
+    u.x = (blockIdx.x * RLE_COLS + threadIdx.x) * VEC;
     if (u.x >= W) return false;
     const int seg_h = (H + RLE_SEG - 1) / RLE_SEG;
     u.y0 = blockIdx.y * seg_h;
     u.y1 = min(H, u.y0 + seg_h);
-    u.prev = false;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) u.prev[j] = false;
     if (u.y0 < u.y1) {
-        if (u.y0 > 0) u.prev = mask[(size_t)(u.y0 - 1) * W + u.x] != 0;
-        else if (u.x > 0) u.prev = mask[(size_t)(H - 1) * W + u.x - 1] != 0;
+        if (u.y0 > 0) {
+            rle_load_row<VEC>(mask + (size_t)(u.y0 - 1) * W, u.x, W, u.prev);
+        } else {            // top of a column: the stream comes from the bottom of the column to the left
+            bool last[VEC];
+            rle_load_row<VEC>(mask + (size_t)(H - 1) * W, u.x, W, last);
+#pragma unroll
+            for (int j = 1; j < VEC; ++j) u.prev[j] = last[j - 1];
+            u.prev[0] = u.x > 0 ? mask[(size_t)(H - 1) * W + u.x - 1] != 0 : false;
+        }
     }
     return true;
 }
 
+template <int VEC>
 __global__ void __launch_bounds__(RLE_COLS) rle_count_kernel(const unsigned char *__restrict__ masks, int H, int W,
                                                               int *__restrict__ unit_offsets) {
     const unsigned char *mask = masks + (size_t)blockIdx.z * H * W;
-    RleUnit u;
-    if (!rle_unit(mask, H, W, u)) return;
-    int cnt = 0;
-    bool prev = u.prev;
+    RleUnits<VEC> u;
+    if (!rle_units<VEC>(mask, H, W, u)) return;
+    int cnt[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) cnt[j] = 0;
+#pragma unroll 4
     for (int y = u.y0; y < u.y1; ++y) {
-        const bool v = mask[(size_t)y * W + u.x] != 0;
-        cnt += v != prev;
-        prev = v;
+        bool v[VEC];
+        rle_load_row<VEC>(mask + (size_t)y * W, u.x, W, v);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            cnt[j] += v[j] != u.prev[j];
+            u.prev[j] = v[j];
+        }
     }
-    unit_offsets[(size_t)blockIdx.z * W * RLE_SEG + u.x * RLE_SEG + blockIdx.y] = cnt;
+    int *out = unit_offsets + (size_t)blockIdx.z * W * RLE_SEG + (size_t)u.x * RLE_SEG + blockIdx.y;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) out[j * RLE_SEG] = cnt[j];
 }
 
 __global__ void __launch_bounds__(1024) rle_scan_units_kernel(int *__restrict__ unit_offsets, int n_units, int *__restrict__ n_runs) {
@@ -130,17 +160,26 @@ __global__ void __launch_bounds__(1024) rle_scan_units_kernel(int *__restrict__ 
     if (threadIdx.x == 0) n_runs[blockIdx.x] = total;
 }
 
+template <int VEC>
 __global__ void __launch_bounds__(RLE_COLS) rle_emit_kernel(const unsigned char *__restrict__ masks, int H, int W,
                                                              const int *__restrict__ unit_offsets, uint32_t *__restrict__ positions) {
     const unsigned char *mask = masks + (size_t)blockIdx.z * H * W;
-    RleUnit u;
-    if (!rle_unit(mask, H, W, u)) return;
-    uint32_t *out = positions + (size_t)blockIdx.z * H * W + unit_offsets[(size_t)blockIdx.z * W * RLE_SEG + u.x * RLE_SEG + blockIdx.y];
-    bool prev = u.prev;
+    RleUnits<VEC> u;
+    if (!rle_units<VEC>(mask, H, W, u)) return;
+    const int *offs = unit_offsets + (size_t)blockIdx.z * W * RLE_SEG + (size_t)u.x * RLE_SEG + blockIdx.y;
+    uint32_t *base = positions + (size_t)blockIdx.z * H * W;
+    uint32_t *out[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) out[j] = base + offs[j * RLE_SEG];
+#pragma unroll 4
     for (int y = u.y0; y < u.y1; ++y) {
-        const bool v = mask[(size_t)y * W + u.x] != 0;
-        if (v != prev) *out++ = (uint32_t)u.x * (uint32_t)H + (uint32_t)y;
-        prev = v;
+        bool v[VEC];
+        rle_load_row<VEC>(mask + (size_t)y * W, u.x, W, v);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            if (v[j] != u.prev[j]) *out[j]++ = (uint32_t)(u.x + j) * (uint32_t)H + (uint32_t)y;
+            u.prev[j] = v[j];
+        }
     }
 }
 
@@ -279,10 +318,14 @@ extern "C" int vnext_rle_encode(const unsigned char *masks, int n_masks, int H, 
     int *chunk_chars = reinterpret_cast<int *>(ws + l.chunk_chars);
     long long *chunk_offsets = reinterpret_cast<long long *>(ws + l.chunk_offsets);
     const int hw = H * W;
-    const dim3 unit_grid((W + RLE_COLS - 1) / RLE_COLS, RLE_SEG, n_masks), chunk_grid(l.n_chunks, n_masks);
-    rle_count_kernel<<<unit_grid, RLE_COLS, 0, st>>>(masks, H, W, unit_offsets);
+    const bool vec4 = W % 4 == 0 && ((uintptr_t)masks & 3) == 0;         // every row (and every mask) starts 4-byte aligned
+    const int cols_per_cta = RLE_COLS * (vec4 ? 4 : 1);
+    const dim3 unit_grid((W + cols_per_cta - 1) / cols_per_cta, RLE_SEG, n_masks), chunk_grid(l.n_chunks, n_masks);
+    if (vec4) rle_count_kernel<4><<<unit_grid, RLE_COLS, 0, st>>>(masks, H, W, unit_offsets);
+    else rle_count_kernel<1><<<unit_grid, RLE_COLS, 0, st>>>(masks, H, W, unit_offsets);
     rle_scan_units_kernel<<<n_masks, 1024, 0, st>>>(unit_offsets, l.n_units, n_runs);
-    rle_emit_kernel<<<unit_grid, RLE_COLS, 0, st>>>(masks, H, W, unit_offsets, positions);
+    if (vec4) rle_emit_kernel<4><<<unit_grid, RLE_COLS, 0, st>>>(masks, H, W, unit_offsets, positions);
+    else rle_emit_kernel<1><<<unit_grid, RLE_COLS, 0, st>>>(masks, H, W, unit_offsets, positions);
     rle_chunk_chars_kernel<<<chunk_grid, 256, 0, st>>>(positions, n_runs, hw, l.n_chunks, chunk_chars);
     rle_scan_chunks_kernel<<<1, 1024, 0, st>>>(chunk_chars, l.n_chunks, n_masks, chunk_offsets, char_offsets);
     rle_write_chars_kernel<<<chunk_grid, 256, 0, st>>>(positions, n_runs, hw, l.n_chunks, chunk_offsets, chars, chars_capacity);

@@ -191,7 +191,6 @@ def video_inference(outputs, tracker, ori_size, image_size, select_thres=0.1, te
     h, w = masks.shape[-2:]
     prob = logits.sigmoid()
     max_score, max_cls = prob.max(2)                                            # [T,nq]
-    binary = (masks.sigmoid() > 0.5).flatten(2)                                 # [T,nq,h*w]
     prob_host = prob.cpu()
     video = {}                                                                  # id -> {"slots": [q or None]*T, "valid"}
     for t in range(T):
@@ -202,7 +201,8 @@ def video_inference(outputs, tracker, ori_size, image_size, select_thres=0.1, te
             keep = tvops.batched_nms(_xyxy(boxes[t][idx]), max_score[t][idx], max_cls[t][idx], 0.9)
             idx = idx[keep]                                                     # descending score
         cand = torch.cat([boxes[t][idx], max_score[t][idx, None], max_cls[t][idx, None].float(), embeds[t][idx],
-                          pairwise_mask_iou(binary[t][idx])], 1).cpu()          # ONE copy per frame
+                          pairwise_mask_iou((masks[t][idx].sigmoid() > 0.5).flatten(1))], 1).cpu()   # ONE copy per frame
+        # (binary masks of the frame's CANDIDATES only: the whole video's [T, nq, h, w] sigmoid is never materialised)
         n = len(idx)
         det_bboxes, det_labels = cand[:, :5], cand[:, 5].long()
         C = embeds.shape[-1]
