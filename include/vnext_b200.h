@@ -33,8 +33,10 @@ extern "C" {
 enum {
     VNEXT_F32 = 0,  /* everything fp32 (reference: AT_DISPATCH_FLOATING_TYPES float) */
     VNEXT_F64 = 1,  /* everything fp64 (reference: double; used by gradcheck) */
-    VNEXT_BF16 = 2  /* value/output(/grad_output/grad_value) bf16; sampling_loc, attn_weight and
+    VNEXT_BF16 = 2, /* value/output(/grad_output/grad_value) bf16; sampling_loc, attn_weight and
                        their grads stay fp32; accumulation fp32.  New: the reference has no bf16. */
+    VNEXT_F16 = 3   /* IEEE fp16 storage — vnext_linear_tc only (a + weight and/or out): 11 significant bits, i.e. at least what
+                       a TF32 MMA keeps of an fp32 operand, at half the bytes; outputs saturate at +-65504 */
 };
 
 enum {
@@ -169,7 +171,8 @@ int vnext_linear_tf32(const float *a, int lda, const float *weight, const float 
 
 /*
  * Same kernel, operand / output formats chosen by the caller (bf16 activations end to end; BASELINE config 4):
- *   in_dtype  (VNEXT_F32 | VNEXT_BF16): element type of `a` AND `weight` (fp32 -> kind::tf32, bf16 -> kind::f16 MMAs)
+ *   in_dtype  (VNEXT_F32 | VNEXT_BF16 | VNEXT_F16): element type of `a` AND `weight` (fp32 -> kind::tf32, bf16 / fp16 ->
+ *             kind::f16 MMAs); out_dtype may be VNEXT_F16 too (no residual then)
  *   out_dtype (VNEXT_F32 | VNEXT_BF16): element type of `out` AND `residual`
  * bias, bias2d, LayerNorm gamma/beta and all accumulation / statistics stay fp32.  bf16 rows (a, weight, out, residual)
  * must be 16-byte aligned with pitches that are multiples of 8 elements.  The reference has no bf16 path; its AMP

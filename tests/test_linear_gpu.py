@@ -219,3 +219,42 @@ def test_conv3x3_bf16(T, H, W, Cin, Cout):
     assert (out.double() - ref).abs().max().item() < 2e-5 * scale
     out = conv3x3(x, wk, b, relu=True)
     assert out.dtype == torch.bfloat16 and (out.double() - ref.clamp(min=0)).abs().max().item() < 5e-3 * scale
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 256), (1000, 1024, 256), (97800, 1024, 256), (513, 256, 1024)])
+def test_fp16_output_from_tf32_operands_and_saturation(M, N, K):
+    """The tf32 mode's FFN1: fp32 operands (TF32 MMAs), output stored as IEEE fp16 (round to nearest, saturating)."""
+    from vnext_b200.linear import linear
+    x, w, b = _mk(M, N, K, 11)
+    ref = F.linear(x.double(), w.double(), b.double()).clamp(min=0)
+    out = linear(x, w, b, relu=True, out_dtype=torch.float16)
+    assert out.dtype == torch.float16 and out.shape == (M, N)
+    scale = ref.abs().max().item()
+    assert (out.double() - ref).abs().max().item() < 2.6e-3 * scale            # TF32 products (2e-3) + one fp16 rounding (2^-11)
+    big = linear(x * 1e5, w, b, out_dtype=torch.float16)                        # |values| far above 65504: saturate, never inf
+    assert torch.isfinite(big).all() and big.abs().max().item() == 65504.0
+    with pytest.raises(RuntimeError, match="fp16 output cannot carry a residual"):
+        linear(x, w, b, residual=torch.zeros(M, N, device="cuda", dtype=torch.float16), out_dtype=torch.float16)
+
+
+@pytest.mark.parametrize("M,K", [(128, 256), (333, 1024), (97800, 1024)])
+def test_fp16_operands_residual_layernorm(M, K):
+    """The tf32 mode's FFN2: fp16 hidden x fp16 weight (kind::f16, fp32 accumulate) + fp32 residual + LayerNorm -> fp32;
+    exact products of the fp16-rounded operands: only accumulation-order error vs the float64 reference on the same inputs."""
+    from vnext_b200.linear import linear
+    x, w, b = _mk(M, 256, K, 12)
+    x = x.clamp(min=0)                                                         # post-ReLU hidden
+    g = torch.Generator().manual_seed(13)
+    res = torch.randn(M, 256, generator=g).cuda()
+    gamma = (torch.rand(256, generator=g) + 0.5).cuda()
+    beta = (torch.randn(256, generator=g) * 0.1).cuda()
+    xh, wh = x.half(), w.half()
+    lin = F.linear(xh.double(), wh.double(), b.double())
+    out = linear(xh, wh, b, out_dtype=torch.float32)
+    assert (out.double() - lin).abs().max().item() < 2e-5 * lin.abs().max().item()
+    ref = F.layer_norm(res.double() + lin, (256,), gamma.double(), beta.double(), 1e-5)
+    out = linear(xh, wh, b, residual=res, ln_weight=gamma, ln_bias=beta, out_dtype=torch.float32)
+    assert out.dtype == torch.float32 and (out.double() - ref).abs().max().item() < 1e-4
+    # and against the all-fp32 operands the TF32 path would have rounded itself: same 2e-3 class
+    full = F.layer_norm(res.double() + F.linear(x.double(), w.double(), b.double()), (256,), gamma.double(), beta.double(), 1e-5)
+    assert (out.double() - full).abs().max().item() < 4e-3

@@ -5,7 +5,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libvnext_b200.so")
 
-F32, F64, BF16 = 0, 1, 2
+F32, F64, BF16, F16 = 0, 1, 2, 3
 
 _lib = None
 

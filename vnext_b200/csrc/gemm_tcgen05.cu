@@ -20,6 +20,7 @@
 //                                LayerNorm with thread-local statistics, no cross-thread reduction)
 //   * persistent grid, static round-robin over (m, n) tiles, n fastest so neighbouring CTAs share A in L2.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 
@@ -142,6 +143,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<const uint32_t *>(&h);
 }
+// fp16 with saturation to the largest finite value (an overflowing activation must not become inf)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
 
 // K-major operand tile in shared memory, 128-byte rows, SWIZZLE_128B (8 rows x 128 B = 1024-B atoms):
 //   start address >> 4 | LBO (ignored for swizzled K-major) = 1 | SBO = 1024 B between 8-row groups | version 1 | layout 2
@@ -168,6 +174,7 @@ struct GemmParams {
     const float *bias2d;     // [period, ldb2] or null: added as bias2d[row % period][col] (geometry-dependent bias)
     int period, ldb2;
     int pdl;                 // launched with programmatic stream serialization (see the kernel prologue)
+    int f16_in, f16_out;     // the 16-bit operands / outputs are IEEE fp16 instead of bf16 (same kernels, other formats)
     // MSDA front-end in the epilogue (N == 384 = 8 heads x (4 levels x 4 points x 2 offsets | 4 x 4 logits)): the offsets
     // columns become sampling locations ref + off / (W_l, H_l), the logits columns the softmax over each head's 16 — what
     // MSDeformAttn.forward does between its projection and the sampler (ops/modules/ms_deform_attn.py:98-108)
@@ -338,6 +345,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     } else if (warp == 1 && lane == 0) {
         // ===================== MMA issuer =====================
+        const uint32_t idesc = (KIND == 1 && p.f16_in) ? make_idesc(0, BLOCK_M, BLOCK_N) : IDESC;   // kind::f16 a/b format 0 = F16
         int stage = 0, phase = 0, acc = 0, acc_phase = 0;
         for (int work = first_work; work < num_work; work += work_stride) {
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -350,7 +358,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const uint64_t da = make_smem_desc_sw128(sa), db = make_smem_desc_sw128(sb);
 #pragma unroll
                 for (int k = 0; k < BLOCK_K / UMMA_K; ++k)   // advance 32 B inside the 128-B swizzle row: +2 in 16-B units
-                    umma<KIND>(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0);
+                    umma<KIND>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                 if (csize > 1) umma_commit_mcast(&empty_bar[stage], (uint16_t)3);   // frees the slot in BOTH CTAs
                 else umma_commit(&empty_bar[stage]);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -541,7 +549,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                             }
                             __syncwarp();
                         }
-                        if (OUT16) {
+                        if (OUT16 && p.f16_out) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint4 pk;
+                                pk.x = pack_f16x2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1]));
+                                pk.y = pack_f16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                                pk.z = pack_f16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                                pk.w = pack_f16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                                *reinterpret_cast<uint4 *>(ob + lane * 64 + ((j ^ swz64) << 4)) = pk;
+                            }
+                        } else if (OUT16) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 uint4 pk;
@@ -644,12 +662,13 @@ static int make_tmap_2d(CUtensorMap *tm, int dt, const void *ptr, int rows, int 
         set_error("cuTensorMapEncodeTiled entry point not available");
         return VNEXT_ECUDA;
     }
-    const int esz = dt == VNEXT_BF16 ? 2 : 4;
+    const int esz = dt == VNEXT_BF16 || dt == VNEXT_F16 ? 2 : 4;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = enc(tm, dt == VNEXT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+    CUresult r = enc(tm, dt == VNEXT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : dt == VNEXT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                                             : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                      const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      box_cols * esz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -742,6 +761,8 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUten
 // operand format x output format -> instantiation
 static int launch_any(bool wide, int in_dt, int out_dt, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &to,
                       const CUtensorMap &tr, const GemmParams &p, cudaStream_t stream) {
+    if (in_dt == VNEXT_F16) in_dt = VNEXT_BF16;        // same instantiations: the format is a run-time field (p.f16_in / p.f16_out)
+    if (out_dt == VNEXT_F16) out_dt = VNEXT_BF16;
     if (in_dt == VNEXT_F32 && out_dt == VNEXT_F32)
         return wide ? launch_gemm<256, 3, 0, false>(ta, tb, to, tr, p, stream) : launch_gemm<128, 4, 0, false>(ta, tb, to, tr, p, stream);
     if (in_dt == VNEXT_F32 && out_dt == VNEXT_BF16)
@@ -770,11 +791,18 @@ struct LinearArgs {
 };
 
 static inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline bool is16(int dt) { return dt == VNEXT_BF16 || dt == VNEXT_F16; }     // 2-byte storage types
 
 int linear_tc_device(const LinearArgs &x, cudaStream_t stream) {
     if (x.M == 0 || x.N == 0) return VNEXT_OK;
-    const int oe = x.out_dt == VNEXT_BF16 ? 8 : 4;           // elements per 16 bytes of out / residual
+    const int oe = is16(x.out_dt) ? 8 : 4;                   // elements per 16 bytes of out / residual
     GemmParams p;
+    p.f16_in = x.in_dt == VNEXT_F16;
+    p.f16_out = x.out_dt == VNEXT_F16;
+    if (p.f16_out && x.residual) {
+        set_error("vnext_linear: an fp16 output cannot carry a residual (the residual is read in the output's type; use fp32 / bf16)");
+        return VNEXT_EINVAL;
+    }
     p.M = x.M; p.N = x.N; p.K = x.K; p.bias = x.bias; p.bias2d = x.bias2d; p.period = x.period > 0 ? x.period : 1;
     p.ldb2 = x.ldb2; p.row_mask = x.row_mask; p.mask_cols = x.mask_cols; p.residual = static_cast<const float *>(x.residual);
     p.gamma = x.gamma; p.beta = x.beta; p.out = static_cast<float *>(x.out); p.ldo = x.ldo; p.ldr = x.ldr; p.flags = x.flags;
@@ -798,7 +826,7 @@ int linear_tc_device(const LinearArgs &x, cudaStream_t stream) {
             return VNEXT_EINVAL;
         }
     }
-    const int kbox = x.in_dt == VNEXT_BF16 ? 64 : 32;
+    const int kbox = is16(x.in_dt) ? 64 : 32;
     CUtensorMap ta, tb, to, tr;
     int rc = make_tmap_2d(&ta, x.in_dt, x.a, x.M, x.K, x.lda, BLOCK_M, kbox);
     if (rc) return rc;
@@ -813,8 +841,8 @@ int linear_tc_device(const LinearArgs &x, cudaStream_t stream) {
     // coalesced epilogue through shared memory + TMA needs 16-byte aligned rows of out (and residual)
     p.tma_epi = al16(x.out) && x.ldo % oe == 0 && (!x.residual || (al16(x.residual) && x.ldr % oe == 0));
     if ((x.flags & 0x400) && x.out_dt == VNEXT_F32) p.tma_epi = 0;   // debug: force the direct-store epilogue
-    if (x.out_dt == VNEXT_BF16 && !p.tma_epi) {
-        set_error("vnext_linear: bf16 output / residual rows must be 16-byte aligned (ldo %d, ldr %d)", x.ldo, x.ldr);
+    if (is16(x.out_dt) && !p.tma_epi) {
+        set_error("vnext_linear: bf16 / fp16 output / residual rows must be 16-byte aligned (ldo %d, ldr %d)", x.ldo, x.ldr);
         return VNEXT_EINVAL;
     }
     to = ta;
@@ -844,6 +872,7 @@ int conv3x3_tc_device(int in_dt, int out_dt, const void *x, const void *w, const
     p.M = T * H * W; p.N = Cout; p.K = 9 * Cin; p.bias = bias; p.bias2d = nullptr; p.period = 1; p.ldb2 = 0;
     p.b2_tma = 0;
     p.pdl = 0;
+    p.f16_in = p.f16_out = 0;
     p.msda_ref = nullptr;
     p.row_mask = nullptr; p.mask_cols = 0; p.residual = nullptr; p.gamma = p.beta = nullptr; p.out = static_cast<float *>(out);
     p.ldo = Cout; p.ldr = 0; p.flags = relu ? EPI_RELU : 0; p.eps = 0.f; p.vec_ok = 1; p.tma_epi = 1;
@@ -878,7 +907,7 @@ int stem_conv_device(int out_dt, const float *xpad, const float *w, const float 
     const int Ho = Hp / 2, Wo = Wp / 2;
     GemmParams p;
     p.M = T * Ho * Wo; p.N = Cout; p.K = 7 * 32; p.bias = bias; p.bias2d = nullptr; p.period = 1; p.ldb2 = 0;
-    p.b2_tma = 0; p.pdl = 0; p.msda_ref = nullptr;
+    p.b2_tma = 0; p.pdl = 0; p.f16_in = p.f16_out = 0; p.msda_ref = nullptr;
     p.row_mask = nullptr; p.mask_cols = 0; p.residual = nullptr; p.gamma = p.beta = nullptr; p.out = static_cast<float *>(out);
     p.ldo = Cout; p.ldr = 0; p.flags = relu ? EPI_RELU : 0; p.eps = 0.f; p.vec_ok = 1; p.tma_epi = 1;
     p.conv = 2; p.conv_cin_blocks = 1; p.conv_stride = 2; p.conv_tiles_x = (Wo + 127) / 128; p.conv_tiles_y = Ho;
@@ -950,13 +979,13 @@ static int linear_checked(const char *who, int in_dt, int out_dt, const void *a,
                           const float *bias2d, int bias_period, int ldb2, const unsigned char *row_mask, int mask_cols,
                           const void *residual, int ldr, const float *ln_gamma, const float *ln_beta, float ln_eps, void *out,
                           int ldo, int M, int N, int K, int flags, void *stream) {
-    VNEXT_CHECK_ARG((in_dt == VNEXT_F32 || in_dt == VNEXT_BF16) && (out_dt == VNEXT_F32 || out_dt == VNEXT_BF16),
-                    "%s: dtypes must be fp32 (0) or bf16 (2)", who);
+    VNEXT_CHECK_ARG((in_dt == VNEXT_F32 || is16(in_dt)) && (out_dt == VNEXT_F32 || is16(out_dt)),
+                    "%s: dtypes must be fp32 (0), bf16 (2) or fp16 (3)", who);
     VNEXT_CHECK_ARG(M >= 0 && N >= 0 && K > 0, "%s: bad sizes M=%d N=%d K=%d", who, M, N, K);
     VNEXT_CHECK_ARG(flags >= 0 && flags < 0x800 && !(flags & 0x0f0), "%s: unknown epilogue flags %d", who, flags);
     if (M == 0 || N == 0) return VNEXT_OK;
     VNEXT_CHECK_ARG(a && weight && out, "%s: null pointer", who);
-    const int ie = in_dt == VNEXT_BF16 ? 8 : 4;
+    const int ie = is16(in_dt) ? 8 : 4;
     VNEXT_CHECK_ARG(al16(a) && al16(weight) && lda % ie == 0 && K % ie == 0,
                     "%s: a / weight must be 16-byte aligned with lda and K multiples of %d (TMA)", who, ie);
     VNEXT_CHECK_ARG(!(flags & EPI_RESIDUAL) || residual, "%s: residual flag without residual pointer", who);

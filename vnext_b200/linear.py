@@ -21,13 +21,13 @@ def _rows(t, n):
     return t2 if t2.stride(-1) == 1 else t2.contiguous()
 
 
-_DT = {torch.float32: _cabi.F32, torch.bfloat16: _cabi.BF16}
+_DT = {torch.float32: _cabi.F32, torch.bfloat16: _cabi.BF16, torch.float16: _cabi.F16}
 
 
 def linear(x, weight, bias=None, relu=False, gelu=False, residual=None, ln_weight=None, ln_bias=None, ln_eps=1e-5, out=None,
            bias2d=None, row_mask=None, mask_cols=0, name=None, _debug_flags=0, out_dtype=None):
-    """x and weight share a dtype (fp32 -> TF32 MMAs, bf16 -> bf16 MMAs); out_dtype (default: x's) is also the dtype the
-    residual is read in; bias / bias2d / LayerNorm parameters are fp32."""
+    """x and weight share a dtype (fp32 -> TF32 MMAs, bf16 / fp16 -> kind::f16 MMAs); out_dtype (default: x's) is also the dtype
+    the residual is read in (an fp16 output takes no residual); bias / bias2d / LayerNorm parameters are fp32."""
     if not x.is_cuda:
         raise RuntimeError("vnext_b200.linear: CUDA tensors only (no CPU fallback)")
     K = x.shape[-1]
@@ -35,7 +35,7 @@ def linear(x, weight, bias=None, relu=False, gelu=False, residual=None, ln_weigh
     x2 = _rows(x, K)
     M = x2.shape[0]
     if x.dtype != weight.dtype or x.dtype not in _DT:
-        raise RuntimeError(f"vnext_b200.linear: x ({x.dtype}) and weight ({weight.dtype}) must both be fp32 or both bf16")
+        raise RuntimeError(f"vnext_b200.linear: x ({x.dtype}) and weight ({weight.dtype}) must both be fp32, both bf16 or both fp16")
     if out is None:
         out = torch.empty((M, N), dtype=out_dtype or x.dtype, device=x.device)
     if residual is not None and residual.dtype != out.dtype:
@@ -57,7 +57,9 @@ def linear(x, weight, bias=None, relu=False, gelu=False, residual=None, ln_weigh
     info = {"flops": 2.0 * M * N * K,
             "bytes": float(ie * (M * K + N * K) + oe * M * N * (2 if residual is not None else 1)
                            + (4 * M * N if bias2d is not None else 0))}
-    tag = "tf32" if x.dtype == torch.float32 else "bf16"
+    tag = {torch.float32: "tf32", torch.bfloat16: "bf16", torch.float16: "f16"}[x.dtype]
+    if out.dtype == torch.float16 and x.dtype != torch.float16:
+        tag += "_of16"
     with torch.cuda.device(x.device):
         rc = _cabi.timed_call(
             name or f"linear_{tag}_m{M}_n{N}_k{K}_f{flags}", info, x,
