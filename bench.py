@@ -494,6 +494,7 @@ def own_arm(args, rank, world, local_rank):
                    **({"TFLOPs": round(d["flops"] / d["us"] / 1e6, 1)} if d["flops"] else {})}
                for f, d in sorted(fam.items(), key=lambda kv: -kv[1]["us"])}
     roofline = None
+    ridge = tf32_peak = None
     if fam:
         top = max(fam, key=lambda k: fam[k]["us"])
         d = fam[top]
@@ -559,9 +560,25 @@ def own_arm(args, rank, world, local_rank):
                    "achieved": round(dc["bytes"] / dc["us"] / 1e3, 1), "peak": hbm, "unit": "GB/s",
                    "frac": round(dc["bytes"] / dc["us"] / 1e3 / hbm, 4), "flop_per_byte": round(ai, 1),
                    "traffic": (tr or {}).get(dn)}
+            if ridge is not None and ai > ridge:
+                # above the ridge point: the tensor roof bounds this shape (16-bit operands: the bf16/fp16 peak, else TF32)
+                pk = tflops if dn.startswith(("linear_bf16", "linear_f16", "conv3x3_bf16")) else tf32_peak
+                dom.update({"bound": "tensor", "achieved": round(dc["flops"] / dc["us"] / 1e6, 1), "peak": round(pk, 1),
+                            "unit": "TFLOP/s", "frac": round(dc["flops"] / dc["us"] / 1e6 / pk, 4),
+                            "hbm_frac": round(dc["bytes"] / dc["us"] / 1e3 / hbm, 4)})
             roofline["dominant_call_site"] = dom
         if tr:
             roofline["traffic"] = (tr or {}).get(roofline.get("dominant_call_site", {}).get("call_site")) if top == "gemm_tc_kernel" else tr.get(top)
+            if roofline["traffic"] is None and top == "gemm_tc_kernel":
+                # no capture of the dominant shape: quote the HBM-bound encoder projection that has one (same kernel, per launch)
+                for site in ("linear_tf32_m97800_n384_k256_msda_front", "linear_tf32_m97800_n256_k1024_f6"):
+                    if site in tr and site in gemm_sites:
+                        sc = gemm_sites[site]
+                        roofline["traffic"] = tr[site]
+                        roofline["traffic_call_site"] = {"call_site": site, "avg_us": round(sc["us"] / sc["calls"], 1),
+                                                         "algorithmic_bytes_per_launch": round(sc["bytes"] / sc["calls"]),
+                                                         "frac": round(sc["bytes"] / sc["us"] / 1e3 / hbm, 4)}
+                        break
             roofline["traffic_source"] = tr.get("source")
             if "msda_encoder" in roofline and tr.get("msda_encoder"):
                 roofline["msda_encoder"]["traffic"] = tr["msda_encoder"]
@@ -614,10 +631,11 @@ def own_arm(args, rank, world, local_rank):
                    "l2": "no flush: per-step working set (fp32 weights ~165 MB + activations > 1 GB) exceeds the 126 MB L2",
                    "parallelism": f"{world} independent replicas, no data-path collective",
                    "precision": {"fp32": "fp32 storage, fp32 (cuBLAS/cuDNN) GEMMs",
-                                 "tf32": "fp32 storage, TF32 tcgen05 GEMMs / convs, fp32 accumulate; every dense output within 1e-2 "
-                                         "of its scale vs the fp32 CPU oracle AT THIS GEOMETRY (mask logits 6.2-6.6e-3, class "
-                                         "logits 1.8e-3, boxes 0.9e-3: tests/test_engine_gpu.py::"
-                                         "test_full_size_parity_of_the_benchmarked_modes)",
+                                 "tf32": "fp32 storage, TF32 tcgen05 GEMMs / convs, fp32 accumulate; the encoder's FFN hidden tensor is "
+                                         "stored as IEEE fp16 (11 significant bits = what a TF32 MMA keeps of its operand; FFN2 runs "
+                                         "kind::f16 on it); every dense output within 1e-2 of its scale vs the fp32 CPU oracle AT THIS "
+                                         "GEOMETRY (mask logits 6.0-6.1e-3, class logits 1.2-1.6e-3, boxes 0.8-1.0e-3: "
+                                         "tests/test_engine_gpu.py::test_full_size_parity_of_the_benchmarked_modes)",
                                  "bf16": "bf16 storage + bf16 tcgen05 GEMMs in the backbone / input projection and for the encoder's "
                                          "value / sampled / FFN-hidden tensors; fp32 residual stream, accumulate and statistics, fp32 "
                                          "sampling offsets/locations, TF32 300-query decoder and mask branch; class logits / boxes "
