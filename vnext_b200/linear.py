@@ -56,7 +56,7 @@ def linear(x, weight, bias=None, relu=False, gelu=False, residual=None, ln_weigh
     ie, oe = x.element_size(), out.element_size()
     info = {"flops": 2.0 * M * N * K,
             "bytes": float(ie * (M * K + N * K) + oe * M * N * (2 if residual is not None else 1)
-                           + (4 * M * N if bias2d is not None else 0))}
+                           + (4 * period * N if bias2d is not None else 0))}     # the periodic bias is read from HBM once
     tag = {torch.float32: "tf32", torch.bfloat16: "bf16", torch.float16: "f16"}[x.dtype]
     if out.dtype == torch.float16 and x.dtype != torch.float16:
         tag += "_of16"
@@ -106,7 +106,8 @@ def linear_msda_front(x, weight, bias2d, reference_points, level_hw):
     out = torch.empty((M, 384), dtype=torch.float32, device=x.device)
     wh = (ctypes.c_float * 8)(*[float(v) for hw in level_hw for v in (hw[1], hw[0])])
     ie = x.element_size()
-    info = {"flops": 2.0 * M * 384 * K, "bytes": float(ie * (M * K + 384 * K) + 4 * M * 384 * 2)}
+    info = {"flops": 2.0 * M * 384 * K, "bytes": float(ie * (M * K + 384 * K) + 4 * M * 384 + 4 * bias2d.shape[0] * 384 +
+                                                       32 * bias2d.shape[0])}   # x, W, out, periodic bias, reference points
     tag = "tf32" if x.dtype == torch.float32 else "bf16"
     with torch.cuda.device(x.device):
         rc = _cabi.timed_call(f"linear_{tag}_m{M}_n384_k{K}_msda_front", info, x, lambda: _cabi.lib().vnext_linear_msda_front(
