@@ -60,3 +60,22 @@ def test_split_strings_and_empty_rle_helpers():
     assert out == [{"size": [7, 9], "counts": a.decode()}, {"size": [7, 9], "counts": b.decode()}]
     for h, w in [(7, 9), (720, 1280), (1, 1), (4000, 6000)]:
         assert _empty_rle(h, w) == {"size": [h, w], "counts": R.to_string_scalar([h * w]).decode()}
+
+
+def test_evaluator_record_from_already_encoded_masks_needs_no_device():
+    """instances_to_coco_json_video on mask_format="rle" outputs: pure assembly (ytvis_eval.py:196-211); a frame where the
+    instance is absent (None) gets the all-zero mask's RLE like the reference."""
+    from vnext_b200.seqformer.ytvis_eval import instances_to_coco_json_video
+    h, w = 6, 8
+    m = np.zeros((h, w), np.uint8)
+    m[2:4, 3:6] = 1
+    rle = {"size": [h, w], "counts": R.encode(m)["counts"].decode()}
+    inputs = [{"video_id": 3, "length": 2, "height": h, "width": w}]
+    outputs = {"pred_scores": [0.9, 0.4], "pred_labels": [5, 1], "pred_masks": [[rle, None], [None, rle]]}
+    rec = instances_to_coco_json_video(inputs, outputs)
+    zero = {"size": [h, w], "counts": R.encode(np.zeros((h, w), np.uint8))["counts"].decode()}
+    assert rec == [{"video_id": 3, "score": 0.9, "category_id": 5, "segmentations": [rle, zero]},
+                   {"video_id": 3, "score": 0.4, "category_id": 1, "segmentations": [zero, rle]}]
+    assert (R.decode(R.from_string(rec[0]["segmentations"][0]["counts"]), h, w) == m).all()
+    with pytest.raises(AssertionError):
+        instances_to_coco_json_video(inputs * 2, outputs)
