@@ -24,6 +24,8 @@ class RleEncoder:
         self.chars = torch.empty(self.capacity, dtype=torch.uint8, device=self.device)
 
     def grow(self, capacity):
+        """A larger string buffer (a NEW allocation: never call this on an encoder whose encode() was captured in a CUDA graph —
+        the graph keeps writing the old buffer; make a second encoder instead, as ClipRunner does)."""
         self.capacity = int(capacity)
         self.chars = torch.empty(self.capacity, dtype=torch.uint8, device=self.device)
 

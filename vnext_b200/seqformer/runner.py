@@ -38,7 +38,7 @@ class ClipRunner:
         self.ori_size = tuple(ori_size) if ori_size is not None else (H, W)
         self.topk = topk
         self.mask_format = mask_format
-        self.rle = None
+        self.rle = self._rle_big = None
         self.direct_h2d = False        # measured slower than one staged copy in round 1 (five small copies); kept selectable
         dev = engine.device
         self.frames_dev = torch.zeros(T, 3, H, W, dtype=torch.uint8, device=dev)
@@ -165,13 +165,21 @@ class ClipRunner:
         total = int(self._off_pin[-1])
         first = self._chars_pin.numel()
         chars = self._chars_pin
-        if total > first:                  # rare: long strings (noisy masks) — fetch the rest; overflow -> re-encode, larger buffer
+        if total > first:                  # long strings (noisy masks): fetch all of them in a second copy
             with torch.cuda.stream(self.stream):
+                src = self.rle.chars
                 if total > self.rle.capacity:
-                    self.rle.grow(total)
-                    self.rle.encode(self.masks)       # eager, after the graph: this runner has one clip in flight
+                    # the strings outgrew the buffer the captured graph writes (its address and capacity are baked into the
+                    # graph, so that encoder is left alone): encode again, eagerly, into a larger buffer — same masks, same
+                    # offsets; this runner has one clip in flight, self.masks is still this clip's
+                    from ..rle import RleEncoder
+                    if self._rle_big is None or self._rle_big.capacity < total:
+                        k, t, oh, ow = self.masks.shape
+                        self._rle_big = RleEncoder(k * t, oh, ow, self.masks.device, capacity=total + total // 4)
+                    self._rle_big.encode(self.masks)
+                    src = self._rle_big.chars
                 chars = torch.empty(total, dtype=torch.uint8, pin_memory=True)
-                chars.copy_(self.rle.chars[:total], non_blocking=True)
+                chars.copy_(src[:total], non_blocking=True)
             self.stream.synchronize()
         self.d2h_bytes = self.scores.numel() * 4 + self._off_pin.numel() * 8 + max(total, first)
         k, t, oh, ow = self.masks.shape
